@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""
+bench.py -- output voxels/s of the dense Lucas-Kanade hot path (calc_flow3D / calc_flow2D).
+
+    python bench.py --gpus N --steps K --warmup W [--workload cfg4] [--precision fp64]
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over the workload's whole synthetic time-lapse: every output
+timepoint (Nt - 2*ceil(3 tSig) of them) is computed once, sharded by output timepoint across the N
+ranks (strong scaling; no data-path collective).  `value` = output voxels of all ranks / max-over-ranks
+device time, inputs resident in HBM.  `e2e` = the same metric through the drop-in Python call
+calc_flow3D(host window) -> host arrays, host<->device copies inside the timed region, on a bounded
+number of timepoints of the same volume shape.  `cpu_baseline` / `--impl reference` = the reference's
+NumPy/SciPy algorithm (oracle port using the reference's own scipy.ndimage.correlate1d and
+numpy.linalg.eigvals calls) on the box's host cores, on a z/y/x-cropped sample of the same workload.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# BASELINE.json configs; uint16 camera-like input
+WORKLOADS = {
+    'cfg1': dict(shape=(7, 32, 128, 128), sig=(1, 1, 4)),
+    'cfg2': dict(shape=(31, 2048, 2048), sig=(1.5, 1, 4)),
+    'cfg3': dict(shape=(31, 64, 512, 512), sig=(3, 2, 6)),
+    'cfg4': dict(shape=(61, 128, 1024, 1024), sig=(3, 1, 4)),   # the configuration the metric is quoted on
+}
+METRIC = 'output voxels/s (vx,vy,vz,rel) 1024x1024x128 stack'
+UNIT = 'voxels/s'
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def alg_bytes_per_voxel(sig, ndim, precision, in_itemsize=2):
+    """one calc_flow call reads its Kt-frame window once and writes its outputs once."""
+    kt = 2 * math.ceil(3 * sig[1]) + 1
+    return kt * in_itemsize + (ndim + 1) * (8 if precision == 'fp64' else 4)
+
+
+def alg_fma_per_voxel(sig, ndim):
+    """SURVEY.md 8(d) second roof: FMAs of the direct separable evaluation."""
+    kr = 2 * math.ceil(3 * sig[0]) + 1
+    ks = 2 * math.ceil(3 * sig[0] / 4) + 1
+    kt = 2 * math.ceil(3 * sig[1]) + 1
+    kw = 2 * math.ceil(3 * sig[2]) + 1
+    if ndim == 3:
+        return (kt - 1) + 3 * kr + 3 * kr + 6 * ks + 9 + 27 * kw + 120
+    return (kt - 1) + 2 * kr + 2 * kr + 2 * ks + 5 + 10 * kw + 30
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(',')]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    img, sig, ndim = args
+    from oracle import lk_oracle as orc
+    t0 = time.perf_counter()
+    if ndim == 3:
+        orc.lk_flow3d(img, *sig, rel_mode='reference', use_scipy=True)
+    else:
+        orc.lk_flow2d(img, *sig, use_scipy=True)
+    return time.perf_counter() - t0
+
+
+def cpu_sample(workload, target_voxels, seed=0):
+    """A cropped window of the workload (same sigmas, same dtype, same blob model) for the CPU arm."""
+    from opticalflow3d_dev_b200.synth import make_stack
+    w = WORKLOADS[workload]
+    sig = w['sig']
+    kt = 2 * math.ceil(3 * sig[1]) + 1
+    sp = list(w['shape'][1:])
+    while np.prod(sp) > target_voxels:      # halve the largest axis until it fits
+        i = int(np.argmax(sp))
+        sp[i] = max(8, sp[i] // 2)
+        if all(s <= 8 for s in sp):
+            break
+    return make_stack((kt,) + tuple(sp), seed=1000 + seed, dtype=np.uint16), sig, len(sp)
+
+
+def run_cpu(workload, cores, steps, warmup, target_voxels):
+    """Reference algorithm on `cores` processes, one cropped window each per step."""
+    import multiprocessing as mp
+    jobs = [cpu_sample(workload, target_voxels, seed=i) for i in range(cores)]
+    vox = sum(int(np.prod(j[0].shape[1:])) for j in jobs)
+    times = []
+    if cores == 1:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter(); _cpu_worker(jobs[0]); dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    else:
+        with mp.get_context('fork').Pool(cores) as pool:
+            for it in range(warmup + steps):
+                t0 = time.perf_counter(); pool.map(_cpu_worker, jobs); dt = time.perf_counter() - t0
+                if it >= warmup:
+                    times.append(dt)
+    sample = '%d window(s) of %s uint16, sigmas %s' % (cores, 'x'.join(map(str, jobs[0][0].shape)), jobs[0][1])
+    return vox * len(times) / sum(times), float(np.mean(times)) * 1e3, sample
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ.setdefault(k, '1')       # the reference is single-threaded; we scale by processes instead
+    cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1)))
+    w = WORKLOADS[args.workload]
+    # ~0.12 Mvox/s/core for the 3D path (BASELINE.md probe): ~0.5 Mvox per core per step is ~4-5 s
+    v, ms, sample = run_cpu(args.workload, cores, args.steps, min(args.warmup, 1), args.cpu_voxels)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'shape': list(w['shape']), 'sigmas': list(w['sig']), 'input_dtype': 'uint16',
+                   'note': 'CPU arm: each step = one cropped window per core (bounded sample); warmup capped at 1'},
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def gpu_arm(args, rank, world, local_rank):
+    import ctypes as C
+    import torch
+    from opticalflow3d_dev_b200.build import build_library
+    if rank == 0:
+        build_library()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        dist.barrier()
+    from opticalflow3d_dev_b200 import _lib
+    from opticalflow3d_dev_b200.calc_flow import calc_flow2D, calc_flow3D
+    from opticalflow3d_dev_b200.taps import flow_taps
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    w = WORKLOADS[args.workload]
+    shape, sig = tuple(w['shape']), w['sig']
+    ndim = len(shape) - 1
+    nt = shape[0] if args.timepoints is None else min(shape[0], args.timepoints + 2 * math.ceil(3 * sig[1]))
+    sp = shape[1:]
+    nz = sp[0] if ndim == 3 else 1
+    ny, nx = sp[-2], sp[-1]
+    vol = int(np.prod(sp))
+    rt = math.ceil(3 * sig[1])
+    kt = 2 * rt + 1
+    outs_all = list(range(rt, nt - rt))                         # output timepoints of the time-lapse
+    per = [len(outs_all) // world + (1 if r < len(outs_all) % world else 0) for r in range(world)]
+    lo = sum(per[:rank]); mine = outs_all[lo:lo + per[rank]]
+
+    ctx = _lib.get_context(local_rank)
+    lib = ctx.lib
+    tp = flow_taps(*sig)
+    taps, keep = _lib.make_taps(tp)
+    prec = _lib.FP64 if args.precision == 'fp64' else _lib.FP32
+    odt = torch.float64 if args.precision == 'fp64' else torch.float32
+    flags = _lib.FLAG_GENERIC if args.generic else 0
+
+    # this rank's frames [mine[0]-rt, mine[-1]+rt], generated on the device (uint16 stored in int16 tensors)
+    nloc = (len(mine) + 2 * rt) if mine else 0
+    frames = torch.empty((max(nloc, 1), nz, ny, nx), dtype=torch.int16, device=dev)
+    torch.cuda.synchronize()
+    if mine:
+        _lib.check(lib.of3d_synth_blobs(ctx.handle, frames.data_ptr(), nloc, nz, ny, nx, mine[0] - rt, 0, 1000 + 4), 'synth')
+    outs = [torch.empty((nz, ny, nx), dtype=odt, device=dev) for _ in range(ndim + 1)]
+    optr = [C.c_void_p(o.data_ptr()) for o in outs]
+    if ndim == 2:
+        optr = [optr[0], optr[1], None, optr[2]]
+    fbytes = vol * 2
+    torch.cuda.synchronize()
+    ctx.set_async(True)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def one_pass():
+        for i in range(len(mine)):
+            ptrs = (C.c_void_p * kt)(*[frames.data_ptr() + (i + k) * fbytes for k in range(kt)])
+            rc = lib.of3d_flow_frames(ctx.handle, ndim, ptrs, _lib.U16, _lib.DEVICE, nz, ny, nx, C.byref(taps), prec, flags,
+                                      optr[0], optr[1], optr[2], optr[3], _lib.DEVICE)
+            _lib.check(rc, 'of3d_flow_frames')
+
+    def barrier():
+        ctx.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_pass()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        one_pass()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    lsum = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
+    ms_total = float(tmax.item())
+    total_vox = len(outs_all) * vol * args.steps
+    value = total_vox / (ms_total * 1e-3)
+    ctx.set_async(False)
+
+    # ---- end-to-end through the drop-in Python call with host (pinned) buffers
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = max(1, min(args.e2e_timepoints, len(mine))) if mine else 0
+        np_odt = np.float64 if args.precision == 'fp64' else np.float32
+        if n_e2e:
+            hwin = _lib.pinned_empty((n_e2e + 2 * rt,) + tuple(sp), np.uint16)
+            hwin[...] = frames[:n_e2e + 2 * rt].reshape(hwin.shape).cpu().numpy().view(np.uint16)
+            hout = tuple(_lib.pinned_empty(tuple(sp), np_odt) for _ in range(ndim + 1))
+            fn = calc_flow3D if ndim == 3 else calc_flow2D
+            kw = dict(precision=args.precision, device=local_rank, out=hout, generic=args.generic)
+            fn(hwin[0:kt], *sig, **kw)                              # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            fn(hwin[i:i + kt], *sig, **kw)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        nn = torch.tensor([float(n_e2e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+        e2e = {'value': float(nn.item()) * vol / float(tt.item()), 'unit': UNIT,
+               'h2d_bytes_per_step': int(kt * vol * 2 * nn.item()),
+               'd2h_bytes_per_step': int((ndim + 1) * vol * np.dtype(np_odt).itemsize * nn.item()),
+               'timepoints': int(nn.item()), 'api': 'calc_flow%dD(host ndarray window) -> host ndarrays (pinned)' % ndim}
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    bpv = alg_bytes_per_voxel(sig, ndim, args.precision)
+    ach = value * bpv / 1e9 / world                             # per-GPU algorithmic GB/s
+    fma = alg_fma_per_voxel(sig, ndim)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f64' if args.precision == 'fp64' else 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'shape': [nt] + list(sp), 'sigmas': list(sig), 'input_dtype': 'uint16',
+                   'output_timepoints_per_step': len(outs_all), 'sharding': 'output timepoint, no collective',
+                   'l2': 'inputs+intermediates per timepoint (>= %.1f GB) exceed the 126 MB L2' % (kt * vol * 2 / 1e9),
+                   'kernels': 'generic' if args.generic else 'default'},
+        'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+                     'peak_source': peak_src, 'alg_bytes_per_voxel': bpv, 'per': 'GPU, whole per-timepoint pipeline',
+                     'fp_pipe': {'alg_fma_per_voxel': fma, 'achieved_tfma_per_s': value * fma / 1e12 / world,
+                                 'note': 'binding roof is the CUDA-core FMA pipe, see DESIGN.md'}},
+        'clocks': clocks, 'gpu_launches': int(lsum.item()), 'e2e': e2e,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, _, sample = run_cpu(args.workload, 1, 1, 0, args.cpu_voxels * 4)
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg4', choices=sorted(WORKLOADS))
+    ap.add_argument('--precision', default='fp64', choices=['fp64', 'fp32'])
+    ap.add_argument('--timepoints', type=int, default=None, help='limit the number of output timepoints (debug)')
+    ap.add_argument('--generic', action='store_true', help='force the generic kernels')
+    ap.add_argument('--e2e-timepoints', type=int, default=2)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-voxels', type=int, default=400_000, help='voxels per core per CPU step')
+    ap.add_argument('--cpu-cores', type=int, default=None)
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        reference_arm(args, rank)
+        return
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+               '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 1000)] + sys.argv
+        os.execv(sys.executable, cmd)
+    gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,158 @@
+/*
+ * of3d.h -- C ABI of libof3d.so: dense Gaussian-weighted Lucas-Kanade optical flow
+ * (2D+t and 3D+t) on NVIDIA B200 (sm_100a).
+ *
+ * The reference (ScientistRachel/OpticalFlow3D_dev) has no FFI: its operator
+ * interface for this path is two Python functions.  Each entry point below cites
+ * the reference interface it replaces (paths relative to the reference root).
+ *
+ *   of3d_flow3d  <->  calc_flow3D(images, xyzSig, tSig, wSig)   src/Python/calc_flow.py:175-360
+ *   of3d_flow2d  <->  calc_flow2D(images, xySig,  tSig, wSig)   src/Python/calc_flow.py:18-173
+ *
+ * The sigmas never cross this boundary: the host evaluates the reference's tap
+ * expressions (calc_flow.py:72-97 / 230-263) in float64 and passes the five tap
+ * vectors, so the doubles are bit-identical to the reference's.
+ *
+ * Conventions: plain pointers and sizes only; volumes are C-contiguous
+ * (t, z, y, x) with x fastest; every function returns OF3D_OK (0) or a negative
+ * code and stores a message retrievable with of3d_last_error() (thread-local).
+ * Calls are synchronous with respect to the host unless stated otherwise.  One
+ * context per (host thread, device); a context is not thread-safe.
+ */
+#ifndef OF3D_H
+#define OF3D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OF3D_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define OF3D_API __attribute__((visibility("default")))
+#else
+#define OF3D_API
+#endif
+
+/* status codes */
+#define OF3D_OK 0
+#define OF3D_ERR_ARG (-1)     /* bad argument (shape, dtype, taps, null pointer) */
+#define OF3D_ERR_CUDA (-2)    /* CUDA runtime error */
+#define OF3D_ERR_NOMEM (-3)   /* device or pinned-host allocation failed */
+#define OF3D_ERR_NODEVICE (-4)/* no usable CUDA device: there is NO CPU fallback */
+
+/* element type of the input images (calc_flow.py:67,225 widens any real dtype) */
+#define OF3D_U8 0
+#define OF3D_U16 1
+#define OF3D_I16 2
+#define OF3D_F32 3
+#define OF3D_F64 4
+#define OF3D_I32 5
+#define OF3D_U32 6
+
+/* arithmetic type of the whole pipeline; outputs are written in the same type */
+#define OF3D_FP64 0 /* double: matches the reference to ~1e-12 (bit-exact with OF3D_FLAG_EXACT) */
+#define OF3D_FP32 1 /* float filters and windows, fp64 solve; outputs float */
+
+/* where a buffer lives */
+#define OF3D_HOST 0
+#define OF3D_DEVICE 1
+
+/* flags for of3d_flow3d / of3d_flow2d */
+#define OF3D_FLAG_EXACT 1u    /* generic kernels, scipy's paired summation order, no FMA contraction:
+                                 fp64 flow fields bit-identical to the reference */
+#define OF3D_FLAG_GENERIC 2u  /* force the generic (any tap count) kernels, normal rounding */
+
+/*
+ * The five sampled, un-normalised 1-D filters of the reference, as float64, each of odd length:
+ *   D  x*G_sig(x)/sig^2   derivative filter          calc_flow.py:233,235 (fderiv*gderiv)
+ *   S  G_{sig/4}(y)       narrow orthogonal smoother calc_flow.py:234      (fsmooth)
+ *   G  G_sig(x)           smoother applied to dI/dt  calc_flow.py:253      (fx)
+ *   T  t*G_tSig(t)/tSig^2 temporal derivative        calc_flow.py:254,256 (ft*gt)
+ *   W  G_wSig(w)          Lucas-Kanade window        calc_flow.py:263      (gw)
+ */
+typedef struct of3d_taps {
+    const double* D; int32_t nD;
+    const double* S; int32_t nS;
+    const double* G; int32_t nG;
+    const double* T; int32_t nT;
+    const double* W; int32_t nW;
+} of3d_taps;
+
+typedef struct of3d_ctx of3d_ctx; /* per-device workspace + stream */
+
+OF3D_API int of3d_version(void);
+OF3D_API const char* of3d_last_error(void);
+OF3D_API int of3d_device_count(void);
+
+/* Create / destroy a context on CUDA device `device`.  The context owns a growable device
+ * workspace and one stream.  Fails with OF3D_ERR_NODEVICE when no GPU is present. */
+OF3D_API int of3d_create(int device, of3d_ctx** out);
+OF3D_API int of3d_destroy(of3d_ctx* ctx);
+
+/* Bytes of device workspace one call needs (excluding caller-provided device buffers and,
+ * for host inputs/outputs, the staging copies which are included).  ndim is 2 or 3. */
+OF3D_API size_t of3d_workspace_bytes(int ndim, int64_t nt_taps, int64_t nz, int64_t ny, int64_t nx, int in_dtype,
+                            int precision, int in_mem, int out_mem);
+/* Pre-size the workspace (optional; calls grow it on demand). */
+OF3D_API int of3d_reserve(of3d_ctx* ctx, size_t bytes);
+
+/*
+ * calc_flow3D (calc_flow.py:175-360).
+ *   images : (nt, nz, ny, nx) of in_dtype, host or device (in_mem).  Not modified.
+ *            nt must be odd and >= taps->nT; the centre frame ceil(nt/2)-1 is analysed
+ *            (calc_flow.py:216-223).  Only frames within nT/2 of the centre are read.
+ *   vx,vy,vz,rel : (nz, ny, nx) of double (OF3D_FP64) or float (OF3D_FP32), host or device
+ *            (out_mem), caller-allocated.  rel = smallest eigenvalue of the windowed
+ *            structure tensor (calc_flow.py:352-357), computed in fp64.
+ */
+OF3D_API int of3d_flow3d(of3d_ctx* ctx, const void* images, int in_dtype, int in_mem,
+                int64_t nt, int64_t nz, int64_t ny, int64_t nx,
+                const of3d_taps* taps, int precision, unsigned flags,
+                void* vx, void* vy, void* vz, void* rel, int out_mem);
+
+/* calc_flow2D (calc_flow.py:18-173).  images (nt, ny, nx); vx, vy, rel (ny, nx). */
+OF3D_API int of3d_flow2d(of3d_ctx* ctx, const void* images, int in_dtype, int in_mem,
+                int64_t nt, int64_t ny, int64_t nx,
+                const of3d_taps* taps, int precision, unsigned flags,
+                void* vx, void* vy, void* rel, int out_mem);
+
+/*
+ * Same operators on a window given as taps->nT separate frame pointers (all device, or all
+ * host), frames[k] = time c - nT/2 + k.  This is what a streaming time-lapse driver
+ * (process_flow, calc_flow.py:496-625) calls on its ring of resident frames, so that
+ * overlapping windows never re-upload or re-pack frames.  nz = 1 with ndim = 2 for 2D.
+ */
+OF3D_API int of3d_flow_frames(of3d_ctx* ctx, int ndim, const void* const* frames, int in_dtype, int in_mem,
+                     int64_t nz, int64_t ny, int64_t nx,
+                     const of3d_taps* taps, int precision, unsigned flags,
+                     void* vx, void* vy, void* vz, void* rel, int out_mem);
+
+/* Stream control: the context's stream as a cudaStream_t (for CUDA-event timing by the caller),
+ * asynchronous mode (device in/out only: calls return after enqueueing), and a sync. */
+OF3D_API void* of3d_stream(of3d_ctx* ctx);
+OF3D_API int of3d_set_async(of3d_ctx* ctx, int enable);
+OF3D_API int of3d_sync(of3d_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+OF3D_API int64_t of3d_launch_count(of3d_ctx* ctx);
+
+/* Pinned host buffers for callers that want full-rate host<->device copies. */
+OF3D_API int of3d_host_alloc(void** ptr, size_t bytes);
+OF3D_API int of3d_host_free(void* ptr);
+
+/*
+ * Benchmark utility: fill a device buffer (nt, nz, ny, nx) of uint16 with the synthetic
+ * translating / deforming Gaussian-blob model of SURVEY.md 8(d) (one blob per 16^3 cell,
+ * counter-based hashing, offset 100, Gaussian noise sigma 5).  t0 is the time index of the
+ * first frame so that shards of one time-lapse can be generated independently; z0 likewise.
+ */
+OF3D_API int of3d_synth_blobs(of3d_ctx* ctx, void* dev_out_u16, int64_t nt, int64_t nz, int64_t ny, int64_t nx,
+                     int64_t t0, int64_t z0, uint64_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OF3D_H */

@@ -1,0 +1,163 @@
+"""ctypes binding of libof3d.so (include/of3d.h). There is no CPU fallback: loading fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, 'libof3d.so')
+
+OK = 0
+U8, U16, I16, F32, F64, I32, U32 = range(7)
+FP64, FP32 = 0, 1
+HOST, DEVICE = 0, 1
+FLAG_EXACT, FLAG_GENERIC = 1, 2
+
+DTYPE_CODES = {np.dtype(np.uint8): U8, np.dtype(np.uint16): U16, np.dtype(np.int16): I16,
+               np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32,
+               np.dtype(np.uint32): U32}
+
+
+class Taps(C.Structure):
+    _fields_ = [(n, t) for k in 'DSGTW' for n, t in ((k, C.POINTER(C.c_double)), ('n' + k, C.c_int32))]
+
+
+# every symbol include/of3d.h declares: (restype, argtypes)
+_vp, _i, _i64, _u, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_size_t
+SIGNATURES = {
+    'of3d_version': (_i, []),
+    'of3d_last_error': (C.c_char_p, []),
+    'of3d_device_count': (_i, []),
+    'of3d_create': (_i, [_i, C.POINTER(_vp)]),
+    'of3d_destroy': (_i, [_vp]),
+    'of3d_workspace_bytes': (_sz, [_i, _i64, _i64, _i64, _i64, _i, _i, _i, _i]),
+    'of3d_reserve': (_i, [_vp, _sz]),
+    'of3d_flow3d': (_i, [_vp, _vp, _i, _i, _i64, _i64, _i64, _i64, C.POINTER(Taps), _i, _u, _vp, _vp, _vp, _vp, _i]),
+    'of3d_flow2d': (_i, [_vp, _vp, _i, _i, _i64, _i64, _i64, C.POINTER(Taps), _i, _u, _vp, _vp, _vp, _i]),
+    'of3d_flow_frames': (_i, [_vp, _i, C.POINTER(_vp), _i, _i, _i64, _i64, _i64, C.POINTER(Taps), _i, _u,
+                              _vp, _vp, _vp, _vp, _i]),
+    'of3d_stream': (_vp, [_vp]),
+    'of3d_set_async': (_i, [_vp, _i]),
+    'of3d_sync': (_i, [_vp]),
+    'of3d_launch_count': (_i64, [_vp]),
+    'of3d_host_alloc': (_i, [C.POINTER(_vp), _sz]),
+    'of3d_host_free': (_i, [_vp]),
+    'of3d_synth_blobs': (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, C.c_uint64]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load libof3d.so (building is __graft_entry__.build()'s job). Raises if it is missing."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError('libof3d.so not found at %s: run `python -m opticalflow3d_dev_b200.build` '
+                                   '(this package has no CPU fallback)' % LIB_PATH)
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().of3d_last_error().decode('utf-8', 'replace')
+
+
+def check(rc, what):
+    if rc != OK:
+        raise RuntimeError('%s failed (%d): %s' % (what, rc, last_error()))
+
+
+def make_taps(tp):
+    """dict of float64 arrays -> (Taps struct, keepalive list)."""
+    t = Taps()
+    keep = []
+    for k in 'DSGTW':
+        a = np.ascontiguousarray(tp[k], dtype=np.float64)
+        keep.append(a)
+        setattr(t, k, a.ctypes.data_as(C.POINTER(C.c_double)))
+        setattr(t, 'n' + k, a.size)
+    return t, keep
+
+
+class Context:
+    """One per (host thread, device): owns the device workspace and stream."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self.device = int(device)
+        h = C.c_void_p()
+        check(self.lib.of3d_create(self.device, C.byref(h)), 'of3d_create')
+        self.handle = h
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.of3d_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return self.lib.of3d_stream(self.handle)
+
+    def launch_count(self):
+        return int(self.lib.of3d_launch_count(self.handle))
+
+    def sync(self):
+        check(self.lib.of3d_sync(self.handle), 'of3d_sync')
+
+    def set_async(self, on):
+        check(self.lib.of3d_set_async(self.handle, int(bool(on))), 'of3d_set_async')
+
+
+_tls = threading.local()
+
+
+def get_context(device=None):
+    dev = 0 if device is None else int(device)
+    cache = getattr(_tls, 'ctx', None)
+    if cache is None:
+        cache = _tls.ctx = {}
+    if dev not in cache:
+        cache[dev] = Context(dev)
+    return cache[dev]
+
+
+def pinned_empty(shape, dtype):
+    """NumPy array backed by page-locked host memory (cudaHostAlloc) for full-rate PCIe copies."""
+    lib = load()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    check(lib.of3d_host_alloc(C.byref(p), max(nbytes, 1)), 'of3d_host_alloc')
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib.of3d_host_free(self.ptr)
+            except Exception:
+                pass
+    _PINNED[id(buf)] = (buf, _Owner(p))
+    return arr
+
+
+_PINNED = {}

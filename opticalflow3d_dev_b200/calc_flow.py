@@ -1,0 +1,177 @@
+"""
+calc_flow -- drop-in replacement for the reference module of the same name
+(src/Python/calc_flow.py): dense Gaussian-weighted Lucas-Kanade optical flow for 2D+t and
+3D+t image stacks, computed by hand-written CUDA kernels (sm_100a) through libof3d.so.
+
+Public surface, mirrored from the reference:
+    calc_flow2D(images, xySig=3, tSig=1, wSig=4)      reference calc_flow.py:18
+    calc_flow3D(images, xyzSig=3, tSig=1, wSig=4)     reference calc_flow.py:175
+    process_flow(imDir, imName, fileType="SequenceT", spatialDimensions=3,
+                 xyzSig=3, tSig=1, wSig=4)            reference calc_flow.py:362
+
+Same positional arguments, defaults, SystemExit messages and return conventions.  Extra
+options are keyword-only and default to the reference's behaviour.  There is no CPU
+fallback: without libof3d.so or without a CUDA device every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import sys
+
+import numpy as np
+
+from . import _lib
+from .taps import flow_taps
+
+__all__ = ['calc_flow2D', 'calc_flow3D', 'process_flow']
+
+_MSG_NDIM_2D = 'ERROR: Input image must be a 3D matrix with dimensions N_T, N_Y, N_X'
+_MSG_NDIM_3D = 'ERROR: Input image must be a 3D matrix with dimensions N_T, N_Z, N_Y, N_X'
+_MSG_SHORT = 'ERROR: Input images will lead to edge effects. N_T must be >= 6*tSig+1'
+_MSG_EVEN = 'ERROR: Input images must have an odd number of timepoints. Only the central time point is analyzed'
+
+
+def _validate(images, tSig, ndim, msg_ndim):
+    """The reference's argument checks, same order and text (calc_flow.py:54-64 / 212-222)."""
+    if not (len(images.shape) == ndim):
+        sys.exit(msg_ndim)
+    Nt = images.shape[0]
+    if Nt < 6 * tSig + 1:
+        sys.exit(_MSG_SHORT)
+    if not (Nt % 2):
+        sys.exit(_MSG_EVEN)
+
+
+def _is_cuda_tensor(x):
+    return hasattr(x, 'data_ptr') and getattr(x, 'is_cuda', False)
+
+
+def _default_device():
+    env = os.environ.get('OF3D_DEVICE')
+    if env is not None:
+        return int(env)
+    return 0
+
+
+def _as_supported_host_array(images):
+    a = np.asarray(images)
+    if a.dtype not in _lib.DTYPE_CODES:
+        if a.dtype == np.bool_:
+            a = a.astype(np.uint8)
+        elif a.dtype == np.int8:
+            a = a.astype(np.int16)
+        elif a.dtype.kind in 'uif':
+            a = a.astype(np.float64)      # what the reference does to every input (calc_flow.py:67,225)
+        else:
+            raise TypeError('calc_flow: unsupported image dtype %s' % a.dtype)
+    if not a.dtype.isnative:
+        a = a.astype(a.dtype.newbyteorder('='))
+    return np.ascontiguousarray(a)
+
+
+def _run(images, spatialSig, tSig, wSig, ndim, precision, device, exact, generic, out=None):
+    if precision not in ('fp64', 'fp32'):
+        raise ValueError("precision must be 'fp64' or 'fp32'")
+    if not (spatialSig > 0 and tSig > 0 and wSig > 0):
+        raise ValueError('sigmas must be positive')
+    tp = flow_taps(spatialSig, tSig, wSig)
+    taps, keep = _lib.make_taps(tp)
+    prec = _lib.FP64 if precision == 'fp64' else _lib.FP32
+    flags = (_lib.FLAG_EXACT if exact else 0) | (_lib.FLAG_GENERIC if generic else 0)
+    nout = ndim + 1
+    sp = tuple(int(s) for s in images.shape[1:])
+    nt = int(images.shape[0])
+
+    if _is_cuda_tensor(images):
+        import torch
+        t = images.contiguous()
+        np_dt = np.dtype(str(t.dtype).replace('torch.', ''))
+        if np_dt not in _lib.DTYPE_CODES:
+            raise TypeError('calc_flow: unsupported tensor dtype %s' % t.dtype)
+        dev = t.device.index if device is None else int(device)
+        ctx = _lib.get_context(dev)
+        odt = torch.float64 if precision == 'fp64' else torch.float32
+        torch.cuda.current_stream(dev).synchronize()       # the library runs on its own stream
+        outs = [torch.empty(sp, dtype=odt, device=t.device) for _ in range(nout)]
+        ptrs = [C.c_void_p(o.data_ptr()) for o in outs]
+        in_ptr, code, mem = C.c_void_p(t.data_ptr()), _lib.DTYPE_CODES[np_dt], _lib.DEVICE
+    else:
+        a = _as_supported_host_array(images)
+        ctx = _lib.get_context(_default_device() if device is None else device)
+        odt = np.float64 if precision == 'fp64' else np.float32
+        if out is None:
+            outs = [np.empty(sp, dtype=odt) for _ in range(nout)]
+        else:
+            outs = list(out)
+            if len(outs) != nout or any(not isinstance(o, np.ndarray) or o.shape != sp or o.dtype != odt
+                                        or not o.flags.c_contiguous for o in outs):
+                raise ValueError('out must be %d C-contiguous %s arrays of shape %s' % (nout, np.dtype(odt).name, sp))
+        ptrs = [C.c_void_p(o.ctypes.data) for o in outs]
+        in_ptr, code, mem = C.c_void_p(a.ctypes.data), _lib.DTYPE_CODES[a.dtype], _lib.HOST
+
+    lib = ctx.lib
+    if ndim == 3:
+        rc = lib.of3d_flow3d(ctx.handle, in_ptr, code, mem, nt, sp[0], sp[1], sp[2], C.byref(taps), prec, flags,
+                             ptrs[0], ptrs[1], ptrs[2], ptrs[3], mem)
+    else:
+        rc = lib.of3d_flow2d(ctx.handle, in_ptr, code, mem, nt, sp[0], sp[1], C.byref(taps), prec, flags,
+                             ptrs[0], ptrs[1], ptrs[2], mem)
+    _lib.check(rc, 'of3d_flow%dd' % ndim)
+    del keep
+    return outs
+
+
+def calc_flow2D(images, xySig=3, tSig=1, wSig=4, *, precision='fp64', device=None, exact=False, generic=False,
+                out=None):
+    """
+    Two-dimensional optical flow of the central frame of ``images`` (N_T, N_Y, N_X).
+
+    Mirrors reference calc_flow2D (calc_flow.py:18-173): N_T must be odd and >= 6*tSig+1;
+    (0,0) is the upper-left corner, so positive vy points down.
+
+    Returns (vx, vy, rel): velocities in pixels/frame and the reliability (smallest
+    eigenvalue of the windowed 2x2 structure tensor), each (N_Y, N_X), float64.
+
+    Keyword-only extras (defaults reproduce the reference):
+      precision  'fp64' (matches the reference to ~1e-12) or 'fp32' (float32 filters, float32 outputs)
+      device     CUDA device index (default: $OF3D_DEVICE or 0; a CUDA tensor's own device)
+      exact      use the bit-exact generic kernels (scipy's summation order, no FMA contraction)
+      generic    force the generic kernels with normal rounding
+      out        tuple of preallocated C-contiguous host arrays to receive the results (e.g. pinned
+                 buffers from _lib.pinned_empty); host inputs only
+    A torch CUDA tensor may be passed instead of a NumPy array; outputs are then CUDA tensors.
+    """
+    _validate(images, tSig, 3, _MSG_NDIM_2D)
+    vx, vy, rel = _run(images, xySig, tSig, wSig, 2, precision, device, exact, generic, out)
+    return vx, vy, rel
+
+
+def calc_flow3D(images, xyzSig=3, tSig=1, wSig=4, *, precision='fp64', device=None, exact=False, generic=False,
+                rel_dtype='reference', out=None):
+    """
+    Three-dimensional optical flow of the central z-stack of ``images`` (N_T, N_Z, N_Y, N_X).
+
+    Mirrors reference calc_flow3D (calc_flow.py:175-360).  Returns (vx, vy, vz, rel), each
+    (N_Z, N_Y, N_X); velocities float64.
+
+    rel_dtype='reference' (default) returns the reliability as float32, the dtype the reference
+    returns because it runs the eigen-solver on complex64 (calc_flow.py:355-357); the value is
+    computed in float64 and rounded once.  rel_dtype='float64' keeps the float64 value (what the
+    MATLAB twin's pageeig on doubles gives, calc_flow3D.m:235-236).  Other keyword-only extras as
+    in calc_flow2D.
+    """
+    _validate(images, tSig, 4, _MSG_NDIM_3D)
+    if rel_dtype not in ('reference', 'float64'):
+        raise ValueError("rel_dtype must be 'reference' or 'float64'")
+    vx, vy, vz, rel = _run(images, xyzSig, tSig, wSig, 3, precision, device, exact, generic, out)
+    if rel_dtype == 'reference' and precision == 'fp64' and out is None:
+        rel = rel.float() if _is_cuda_tensor(rel) else rel.astype(np.float32)
+    return vx, vy, vz, rel
+
+
+def process_flow(imDir, imName, fileType="SequenceT", spatialDimensions=3, xyzSig=3, tSig=1, wSig=4, **kwargs):
+    """Time-lapse driver (reference calc_flow.py:362-625); implemented in .timelapse."""
+    from .timelapse import process_flow as _pf
+    return _pf(imDir, imName, fileType, spatialDimensions, xyzSig, tSig, wSig, **kwargs)

@@ -1,0 +1,116 @@
+// Generic (any tap count) kernels: one output element per thread, one pass per launch.
+// They are the always-available fallback for tap counts without a specialised marching
+// kernel, and -- with EXACT = true -- the bit-exact mode: scipy's paired summation order
+// (ni_filters.c NI_Correlate1D, restated in oracle/lk_oracle.py:correlate1d_nearest) with
+// individually rounded multiplies and adds.  Internal header.
+#pragma once
+#include "common.cuh"
+#include "solve.cuh"
+
+namespace of3d {
+
+template <typename T> struct Rn;
+template <> struct Rn<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+};
+template <> struct Rn<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+};
+
+// out[i] = sum_k w[k] * in[clamp(i + k - r)] along one axis of a contiguous volume.
+// `len` = extent of the axis, `stride` = element stride of the axis.
+template <typename T, bool EXACT>
+__global__ void __launch_bounds__(256) corr_axis_generic(const T* __restrict__ in, T* __restrict__ out, int64_t n,
+                                                         int64_t len, int64_t stride, const Filt<T> f) {
+    const int r = f.n / 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pos = (i / stride) % len;
+        const T* base = in + (i - pos * stride);
+        auto at = [&](int64_t p) -> T {
+            p = p < 0 ? 0 : (p >= len ? len - 1 : p);
+            return __ldg(base + p * stride);
+        };
+        T acc;
+        if (EXACT) {
+            if (f.sym > 0) {
+                acc = Rn<T>::mul(at(pos), f.w[r]);
+                for (int l = -r; l < 0; ++l) acc = Rn<T>::add(acc, Rn<T>::mul(Rn<T>::add(at(pos + l), at(pos - l)), f.w[r + l]));
+            } else if (f.sym < 0) {
+                acc = Rn<T>::mul(at(pos), f.w[r]);
+                for (int l = -r; l < 0; ++l) acc = Rn<T>::add(acc, Rn<T>::mul(Rn<T>::sub(at(pos + l), at(pos - l)), f.w[r + l]));
+            } else {
+                const int r2 = f.n - r - 1;
+                acc = Rn<T>::mul(at(pos + r2), f.w[r + r2]);
+                for (int l = -r; l < r2; ++l) acc = Rn<T>::add(acc, Rn<T>::mul(at(pos + l), f.w[r + l]));
+            }
+        } else {
+            acc = T(0);
+            for (int k = 0; k < f.n; ++k) acc = fma(f.w[k], at(pos + k - r), acc);
+        }
+        out[i] = acc;
+    }
+}
+
+// Temporal derivative of the centre frame (calc_flow.py:276-278 / 113-115) and widening of the
+// centre frame to the compute type (calc_flow.py:225 / 67).  frames.p[k] = frame c - r + k.
+template <typename Tin, typename T, bool EXACT>
+__global__ void __launch_bounds__(256) temporal_generic(const FramePtrs frames, const Filt<T> f, T* __restrict__ ic,
+                                                        T* __restrict__ dt0, int64_t n) {
+    const int r = f.n / 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        auto at = [&](int k) -> T { return (T) __ldg(reinterpret_cast<const Tin*>(frames.p[k]) + i); };
+        const T c = at(r);
+        T acc;
+        if (EXACT) {
+            acc = Rn<T>::mul(c, f.w[r]);
+            if (f.sym > 0)
+                for (int l = -r; l < 0; ++l) acc = Rn<T>::add(acc, Rn<T>::mul(Rn<T>::add(at(r + l), at(r - l)), f.w[r + l]));
+            else if (f.sym < 0)
+                for (int l = -r; l < 0; ++l) acc = Rn<T>::add(acc, Rn<T>::mul(Rn<T>::sub(at(r + l), at(r - l)), f.w[r + l]));
+            else {
+                acc = Rn<T>::mul(at(f.n - 1), f.w[f.n - 1]);
+                for (int k = 0; k < f.n - 1; ++k) acc = Rn<T>::add(acc, Rn<T>::mul(at(k), f.w[k]));
+            }
+        } else {
+            acc = T(0);
+            for (int k = 0; k < f.n; ++k) acc = fma(f.w[k], at(k), acc);
+        }
+        ic[i] = c;
+        dt0[i] = acc;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) product_generic(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+                                                       int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = a[i] * b[i];  // a single multiply: identical to NumPy's in either mode
+}
+
+// Window sums, channel-major: w[c*n + i], c in {xx,xy,xz,yy,yz,zz,tx,ty,tz} (3D) / {xx,xy,yy,tx,ty} (2D)
+template <typename T, bool EXACT>
+__global__ void __launch_bounds__(256) solve3_generic(const T* __restrict__ w, int64_t n, T* __restrict__ vx, T* __restrict__ vy,
+                                                      T* __restrict__ vz, T* __restrict__ rel) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Flow3 o = solve3<EXACT>((double)w[i], (double)w[n + i], (double)w[2 * n + i], (double)w[3 * n + i],
+                                      (double)w[4 * n + i], (double)w[5 * n + i], (double)w[6 * n + i],
+                                      (double)w[7 * n + i], (double)w[8 * n + i]);
+        vx[i] = (T)o.vx; vy[i] = (T)o.vy; vz[i] = (T)o.vz; rel[i] = (T)o.rel;
+    }
+}
+
+template <typename T, bool EXACT>
+__global__ void __launch_bounds__(256) solve2_generic(const T* __restrict__ w, int64_t n, T* __restrict__ vx, T* __restrict__ vy,
+                                                      T* __restrict__ rel) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Flow2 o = solve2<EXACT>((double)w[i], (double)w[n + i], (double)w[2 * n + i], (double)w[3 * n + i],
+                                      (double)w[4 * n + i]);
+        vx[i] = (T)o.vx; vy[i] = (T)o.vy; rel[i] = (T)o.rel;
+    }
+}
+
+}  // namespace of3d

@@ -1,0 +1,405 @@
+// libof3d: C ABI + host-side orchestration of the Lucas-Kanade pipeline on one B200.
+// See include/of3d.h for the contract and DESIGN.md for the kernel plan.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_generic.cuh"
+#include "kernels_synth.cuh"
+#include "solve.cuh"
+
+namespace of3d {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+}  // namespace of3d
+
+using namespace of3d;
+
+struct of3d_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char* ws = nullptr;       // device workspace
+    size_t ws_cap = 0;
+    size_t ws_off = 0;        // bump pointer (reset every call)
+    int async = 0;
+    int64_t launches = 0;
+    int sm_count = 148;
+};
+
+namespace of3d {
+
+static size_t dtype_size(int dt) {
+    switch (dt) {
+        case OF3D_U8: return 1;
+        case OF3D_U16: case OF3D_I16: return 2;
+        case OF3D_F32: case OF3D_I32: case OF3D_U32: return 4;
+        case OF3D_F64: return 8;
+        default: return 0;
+    }
+}
+
+static inline size_t align_up(size_t x, size_t a = 512) { return (x + a - 1) / a * a; }
+
+// Scipy's symmetry test (ni_filters.c): odd length and |w[r+i] -/+ w[r-i]| <= DBL_EPSILON
+static int tap_symmetry(const double* w, int n) {
+    if (!(n & 1)) return 0;
+    const int r = n / 2;
+    bool sym = true, asym = true;
+    for (int i = 1; i <= r; ++i) {
+        if (std::fabs(w[r + i] - w[r - i]) > 2.220446049250313e-16) sym = false;
+        if (std::fabs(w[r + i] + w[r - i]) > 2.220446049250313e-16) asym = false;
+    }
+    return sym ? 1 : (asym ? -1 : 0);
+}
+
+template <typename T>
+static Filt<T> make_filt(const double* w, int n) {
+    Filt<T> f;
+    f.n = n;
+    f.sym = tap_symmetry(w, n);
+    for (int i = 0; i < kMaxTaps; ++i) f.w[i] = i < n ? (T)w[i] : T(0);  // rounded once to the compute type
+    return f;
+}
+
+struct Shape {
+    int ndim;           // 2 or 3
+    int64_t nz, ny, nx; // nz == 1 for 2D
+    int64_t n() const { return nz * ny * nx; }
+};
+
+static int grid_for(const of3d_ctx* c, int64_t n, int block = 256) {
+    int64_t g = ceil_div(n, block);
+    int64_t cap = (int64_t)c->sm_count * 32;  // grid-stride beyond this
+    return (int)std::max<int64_t>(1, std::min(g, cap));
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+static int ws_ensure(of3d_ctx* c, size_t bytes) {
+    if (bytes <= c->ws_cap) return OF3D_OK;
+    OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->ws) { OF3D_CUDA_TRY(cudaFree(c->ws)); c->ws = nullptr; c->ws_cap = 0; }
+    cudaError_t e = cudaMalloc(&c->ws, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("device workspace allocation of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+        return OF3D_ERR_NOMEM;
+    }
+    c->ws_cap = bytes;
+    return OF3D_OK;
+}
+
+template <typename P>
+static P* ws_take(of3d_ctx* c, size_t count) {
+    size_t bytes = align_up(count * sizeof(P));
+    P* p = reinterpret_cast<P*>(c->ws + c->ws_off);
+    c->ws_off += bytes;
+    return p;
+}
+
+// Volumes of compute type needed by the generic pipeline (see run_generic)
+static int generic_volumes(int ndim) { return ndim == 3 ? 2 + 2 + 4 + 1 + 9 : 2 + 2 + 3 + 1 + 5; }
+
+static size_t plan_bytes(int ndim, int64_t kt, int64_t n, int in_dtype, int precision, int in_mem, int out_mem) {
+    const size_t ts = precision == OF3D_FP32 ? 4 : 8;
+    size_t b = 0;
+    b += (size_t)generic_volumes(ndim) * align_up((size_t)n * ts);
+    if (in_mem == OF3D_HOST) b += (size_t)kt * align_up((size_t)n * dtype_size(in_dtype));
+    if (out_mem == OF3D_HOST) b += (size_t)(ndim + 1) * align_up((size_t)n * ts);
+    return b + 4096;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic pipeline: reference pass order (y -> x -> z), one pass per launch
+template <typename T, bool EXACT>
+struct GenericPipe {
+    of3d_ctx* c;
+    Shape s;
+    Filt<T> fD, fS, fG, fT, fW;
+
+    void corr(const T* in, T* out, int axis /*0=z,1=y,2=x*/, const Filt<T>& f) {
+        const int64_t n = s.n();
+        const int64_t len = axis == 0 ? s.nz : (axis == 1 ? s.ny : s.nx);
+        const int64_t stride = axis == 0 ? s.ny * s.nx : (axis == 1 ? s.nx : 1);
+        corr_axis_generic<T, EXACT><<<grid_for(c, n), 256, 0, c->stream>>>(in, out, n, len, stride, f);
+        c->launches++;
+    }
+    // out = F_z F_x F_y in   (z skipped in 2D); tmp1/tmp2 scratch
+    void chain(const T* in, T* out, T* t1, T* t2, const Filt<T>& fy, const Filt<T>& fx, const Filt<T>& fz) {
+        corr(in, t1, 1, fy);
+        if (s.ndim == 3) { corr(t1, t2, 2, fx); corr(t2, out, 0, fz); }
+        else corr(t1, out, 2, fx);
+    }
+
+    template <typename Tin>
+    void temporal(const FramePtrs& fp, T* ic, T* dt0) {
+        temporal_generic<Tin, T, EXACT><<<grid_for(c, s.n()), 256, 0, c->stream>>>(fp, fT, ic, dt0, s.n());
+        c->launches++;
+    }
+
+    int run(const FramePtrs& fp, int in_dtype, T* vx, T* vy, T* vz, T* rel) {
+        const int64_t n = s.n();
+        T* ic = ws_take<T>(c, n);
+        T* dt0 = ws_take<T>(c, n);
+        T* t1 = ws_take<T>(c, n);
+        T* t2 = ws_take<T>(c, n);
+        T* dt = ws_take<T>(c, n);
+        T* dx = ws_take<T>(c, n);
+        T* dy = ws_take<T>(c, n);
+        T* dz = s.ndim == 3 ? ws_take<T>(c, n) : nullptr;
+        T* prod = ws_take<T>(c, n);
+        const int nch = s.ndim == 3 ? 9 : 5;
+        T* w = ws_take<T>(c, (size_t)nch * n);
+        switch (in_dtype) {
+            case OF3D_U8: temporal<uint8_t>(fp, ic, dt0); break;
+            case OF3D_U16: temporal<uint16_t>(fp, ic, dt0); break;
+            case OF3D_I16: temporal<int16_t>(fp, ic, dt0); break;
+            case OF3D_F32: temporal<float>(fp, ic, dt0); break;
+            case OF3D_F64: temporal<double>(fp, ic, dt0); break;
+            case OF3D_I32: temporal<int32_t>(fp, ic, dt0); break;
+            case OF3D_U32: temporal<uint32_t>(fp, ic, dt0); break;
+            default: set_error("unsupported input dtype"); return OF3D_ERR_ARG;
+        }
+        chain(dt0, dt, t1, t2, fG, fG, fG);          // calc_flow.py:279 / 116
+        chain(ic, dy, t1, t2, fD, fS, fS);           // :282 / 119
+        chain(ic, dx, t1, t2, fS, fD, fS);           // :285 / 122
+        if (s.ndim == 3) chain(ic, dz, t1, t2, fS, fS, fD);  // :288
+        // products + window, channel order {xx,xy,xz,yy,yz,zz,tx,ty,tz} / {xx,xy,yy,tx,ty}
+        const T* pa[9]; const T* pb[9];
+        if (s.ndim == 3) {
+            const T* A[9] = {dx, dx, dx, dy, dy, dz, dx, dy, dz};
+            const T* B[9] = {dx, dy, dz, dy, dz, dz, dt, dt, dt};
+            for (int i = 0; i < 9; ++i) { pa[i] = A[i]; pb[i] = B[i]; }
+        } else {
+            const T* A[5] = {dx, dx, dy, dx, dy};
+            const T* B[5] = {dx, dy, dy, dt, dt};
+            for (int i = 0; i < 5; ++i) { pa[i] = A[i]; pb[i] = B[i]; }
+        }
+        for (int ch = 0; ch < nch; ++ch) {
+            product_generic<T><<<grid_for(c, n), 256, 0, c->stream>>>(pa[ch], pb[ch], prod, n);
+            c->launches++;
+            chain(prod, w + (size_t)ch * n, t1, t2, fW, fW, fW);  // :300-313 / 133-141
+        }
+        if (s.ndim == 3) solve3_generic<T, EXACT><<<grid_for(c, n), 256, 0, c->stream>>>(w, n, vx, vy, vz, rel);
+        else solve2_generic<T, EXACT><<<grid_for(c, n), 256, 0, c->stream>>>(w, n, vx, vy, rel);
+        c->launches++;
+        return OF3D_OK;
+    }
+};
+
+static int check_taps(const of3d_taps* t) {
+    if (!t) { set_error("taps is null"); return OF3D_ERR_ARG; }
+    const double* p[5] = {t->D, t->S, t->G, t->T, t->W};
+    const int n[5] = {t->nD, t->nS, t->nG, t->nT, t->nW};
+    const char* nm = "DSGTW";
+    for (int i = 0; i < 5; ++i) {
+        if (!p[i] || n[i] < 1 || !(n[i] & 1)) { set_error(std::string("tap vector ") + nm[i] + " must be non-null with odd length"); return OF3D_ERR_ARG; }
+        const int lim = i == 3 ? kMaxFrames : kMaxTaps;
+        if (n[i] > lim) { set_error(std::string("tap vector ") + nm[i] + " is longer than the supported " + std::to_string(lim)); return OF3D_ERR_ARG; }
+    }
+    return OF3D_OK;
+}
+
+template <typename T>
+static int run_typed(of3d_ctx* c, const Shape& s, const FramePtrs& fp, int in_dtype, const of3d_taps* t, unsigned flags,
+                     T* vx, T* vy, T* vz, T* rel) {
+    if (flags & OF3D_FLAG_EXACT) {
+        GenericPipe<T, true> g{c, s, make_filt<T>(t->D, t->nD), make_filt<T>(t->S, t->nS), make_filt<T>(t->G, t->nG),
+                               make_filt<T>(t->T, t->nT), make_filt<T>(t->W, t->nW)};
+        return g.run(fp, in_dtype, vx, vy, vz, rel);
+    }
+    GenericPipe<T, false> g{c, s, make_filt<T>(t->D, t->nD), make_filt<T>(t->S, t->nS), make_filt<T>(t->G, t->nG),
+                            make_filt<T>(t->T, t->nT), make_filt<T>(t->W, t->nW)};
+    return g.run(fp, in_dtype, vx, vy, vz, rel);
+}
+
+static int flow_frames_impl(of3d_ctx* c, int ndim, const void* const* frames, int in_dtype, int in_mem, int64_t nz,
+                            int64_t ny, int64_t nx, const of3d_taps* t, int precision, unsigned flags, void* vx, void* vy,
+                            void* vz, void* rel, int out_mem) {
+    if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
+    if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3"); return OF3D_ERR_ARG; }
+    if (int rc = check_taps(t)) return rc;
+    if (nz < 1 || ny < 1 || nx < 1 || (ndim == 2 && nz != 1)) { set_error("bad volume shape"); return OF3D_ERR_ARG; }
+    if (!dtype_size(in_dtype)) { set_error("unsupported input dtype"); return OF3D_ERR_ARG; }
+    if (precision != OF3D_FP64 && precision != OF3D_FP32) { set_error("precision must be OF3D_FP64 or OF3D_FP32"); return OF3D_ERR_ARG; }
+    if ((in_mem != OF3D_HOST && in_mem != OF3D_DEVICE) || (out_mem != OF3D_HOST && out_mem != OF3D_DEVICE)) { set_error("bad memory space"); return OF3D_ERR_ARG; }
+    if (!frames || !vx || !vy || !rel || (ndim == 3 && !vz)) { set_error("null image or output pointer"); return OF3D_ERR_ARG; }
+    for (int k = 0; k < t->nT; ++k) if (!frames[k]) { set_error("null frame pointer"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+
+    const Shape s{ndim, nz, ny, nx};
+    const int64_t n = s.n();
+    const size_t ts = precision == OF3D_FP32 ? 4 : 8;
+    if (int rc = ws_ensure(c, plan_bytes(ndim, t->nT, n, in_dtype, precision, in_mem, out_mem))) return rc;
+    c->ws_off = 0;
+
+    FramePtrs fp;
+    memset(&fp, 0, sizeof(fp));
+    if (in_mem == OF3D_HOST) {
+        const size_t fb = (size_t)n * dtype_size(in_dtype);
+        for (int k = 0; k < t->nT; ++k) {
+            char* d = ws_take<char>(c, fb);
+            OF3D_CUDA_TRY(cudaMemcpyAsync(d, frames[k], fb, cudaMemcpyHostToDevice, c->stream));
+            fp.p[k] = d;
+        }
+    } else {
+        for (int k = 0; k < t->nT; ++k) fp.p[k] = frames[k];
+    }
+    void* out[4] = {vx, vy, vz, rel};
+    void* dout[4] = {vx, vy, vz, rel};
+    const int nout = ndim + 1;
+    const int oidx3[4] = {0, 1, 2, 3}, oidx2[3] = {0, 1, 3};
+    const int* oidx = ndim == 3 ? oidx3 : oidx2;
+    if (out_mem == OF3D_HOST)
+        for (int i = 0; i < nout; ++i) dout[oidx[i]] = ws_take<char>(c, (size_t)n * ts);
+
+    int rc;
+    if (precision == OF3D_FP64)
+        rc = run_typed<double>(c, s, fp, in_dtype, t, flags, (double*)dout[0], (double*)dout[1], (double*)dout[2], (double*)dout[3]);
+    else
+        rc = run_typed<float>(c, s, fp, in_dtype, t, flags, (float*)dout[0], (float*)dout[1], (float*)dout[2], (float*)dout[3]);
+    if (rc) return rc;
+    OF3D_CUDA_TRY(cudaGetLastError());
+    if (out_mem == OF3D_HOST)
+        for (int i = 0; i < nout; ++i)
+            OF3D_CUDA_TRY(cudaMemcpyAsync(out[oidx[i]], dout[oidx[i]], (size_t)n * ts, cudaMemcpyDeviceToHost, c->stream));
+    if (!(c->async && in_mem == OF3D_DEVICE && out_mem == OF3D_DEVICE)) OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return OF3D_OK;
+}
+
+static int flow_contig(of3d_ctx* c, int ndim, const void* images, int in_dtype, int in_mem, int64_t nt, int64_t nz, int64_t ny,
+                       int64_t nx, const of3d_taps* t, int precision, unsigned flags, void* vx, void* vy, void* vz, void* rel,
+                       int out_mem) {
+    if (int rc = check_taps(t)) return rc;
+    if (!images) { set_error("images is null"); return OF3D_ERR_ARG; }
+    if (nt < t->nT || !(nt & 1)) { set_error("nt must be odd and >= the number of temporal taps"); return OF3D_ERR_ARG; }
+    if (!dtype_size(in_dtype)) { set_error("unsupported input dtype"); return OF3D_ERR_ARG; }
+    const int64_t c0 = (nt + 1) / 2 - 1 - t->nT / 2;  // first frame the centre slice of the t-filter touches
+    const size_t fb = (size_t)nz * ny * nx * dtype_size(in_dtype);
+    const void* frames[kMaxFrames];
+    for (int k = 0; k < t->nT; ++k) frames[k] = (const char*)images + (size_t)(c0 + k) * fb;
+    return flow_frames_impl(c, ndim, frames, in_dtype, in_mem, nz, ny, nx, t, precision, flags, vx, vy, vz, rel, out_mem);
+}
+
+}  // namespace of3d
+
+// =============================================================================================
+extern "C" {
+
+OF3D_API int of3d_version(void) { return OF3D_VERSION; }
+OF3D_API const char* of3d_last_error(void) { return of3d::g_err.c_str(); }
+
+OF3D_API int of3d_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+OF3D_API int of3d_create(int device, of3d_ctx** out) {
+    if (!out) { set_error("out is null"); return OF3D_ERR_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (libof3d has no CPU fallback)");
+        return OF3D_ERR_NODEVICE;
+    }
+    if (device < 0 || device >= n) { set_error("device index out of range"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaSetDevice(device));
+    of3d_ctx* c = new (std::nothrow) of3d_ctx();
+    if (!c) { set_error("out of host memory"); return OF3D_ERR_NOMEM; }
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; set_error(std::string("cudaStreamCreate failed: ") + cudaGetErrorString(e)); return OF3D_ERR_CUDA; }
+    *out = c;
+    return OF3D_OK;
+}
+
+OF3D_API int of3d_destroy(of3d_ctx* c) {
+    if (!c) return OF3D_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->ws) cudaFree(c->ws);
+    delete c;
+    return OF3D_OK;
+}
+
+OF3D_API size_t of3d_workspace_bytes(int ndim, int64_t nt_taps, int64_t nz, int64_t ny, int64_t nx, int in_dtype, int precision,
+                            int in_mem, int out_mem) {
+    if (ndim != 2 && ndim != 3) return 0;
+    return plan_bytes(ndim, nt_taps, nz * ny * nx, in_dtype, precision, in_mem, out_mem);
+}
+
+OF3D_API int of3d_reserve(of3d_ctx* c, size_t bytes) {
+    if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    return ws_ensure(c, bytes);
+}
+
+OF3D_API int of3d_flow3d(of3d_ctx* ctx, const void* images, int in_dtype, int in_mem, int64_t nt, int64_t nz, int64_t ny, int64_t nx,
+                const of3d_taps* taps, int precision, unsigned flags, void* vx, void* vy, void* vz, void* rel, int out_mem) {
+    return flow_contig(ctx, 3, images, in_dtype, in_mem, nt, nz, ny, nx, taps, precision, flags, vx, vy, vz, rel, out_mem);
+}
+
+OF3D_API int of3d_flow2d(of3d_ctx* ctx, const void* images, int in_dtype, int in_mem, int64_t nt, int64_t ny, int64_t nx,
+                const of3d_taps* taps, int precision, unsigned flags, void* vx, void* vy, void* rel, int out_mem) {
+    return flow_contig(ctx, 2, images, in_dtype, in_mem, nt, 1, ny, nx, taps, precision, flags, vx, vy, nullptr, rel, out_mem);
+}
+
+OF3D_API int of3d_flow_frames(of3d_ctx* ctx, int ndim, const void* const* frames, int in_dtype, int in_mem, int64_t nz, int64_t ny,
+                     int64_t nx, const of3d_taps* taps, int precision, unsigned flags, void* vx, void* vy, void* vz, void* rel,
+                     int out_mem) {
+    return flow_frames_impl(ctx, ndim, frames, in_dtype, in_mem, nz, ny, nx, taps, precision, flags, vx, vy, vz, rel, out_mem);
+}
+
+OF3D_API void* of3d_stream(of3d_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+OF3D_API int of3d_set_async(of3d_ctx* c, int enable) {
+    if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
+    c->async = enable ? 1 : 0;
+    return OF3D_OK;
+}
+
+OF3D_API int of3d_sync(of3d_ctx* c) {
+    if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return OF3D_OK;
+}
+
+OF3D_API int64_t of3d_launch_count(of3d_ctx* c) { return c ? c->launches : 0; }
+
+OF3D_API int of3d_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) { set_error("ptr is null"); return OF3D_ERR_ARG; }
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error(std::string("cudaHostAlloc failed: ") + cudaGetErrorString(e)); return OF3D_ERR_NOMEM; }
+    return OF3D_OK;
+}
+
+OF3D_API int of3d_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+    return OF3D_OK;
+}
+
+OF3D_API int of3d_synth_blobs(of3d_ctx* c, void* dev_out_u16, int64_t nt, int64_t nz, int64_t ny, int64_t nx, int64_t t0, int64_t z0,
+                     uint64_t seed) {
+    if (!c || !dev_out_u16 || nt < 1 || nz < 1 || ny < 1 || nx < 1) { set_error("bad argument"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    launch_synth_blobs((uint16_t*)dev_out_u16, nt, nz, ny, nx, t0, z0, seed, c->sm_count, c->stream);
+    c->launches++;
+    OF3D_CUDA_TRY(cudaGetLastError());
+    OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return OF3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// Per-voxel least-squares solve and reliability (always evaluated in fp64). Internal header.
+//
+// 3D: calc_flow.py:337-340 (Sarrus determinant, adjugate solve with the additive eps
+// regulariser) and :352-357 (smallest eigenvalue of the symmetric 3x3 window tensor).
+// 2D: calc_flow.py:154-156 and :163-168.
+#pragma once
+#include "common.cuh"
+
+namespace of3d {
+
+constexpr double kEps = 2.220446049250313e-16;  // np.finfo(float).eps, calc_flow.py:155,338
+
+struct Flow3 { double vx, vy, vz, rel; };
+struct Flow2 { double vx, vy, rel; };
+
+// Smallest eigenvalue of [[xx,xy,xz],[xy,yy,yz],[xz,yz,zz]]: trigonometric closed form
+// (Smith 1961).  The reference runs LAPACK cgeev on complex64 (float32 accuracy); for a
+// real symmetric matrix the eigenvalues are real and the lexicographic complex minimum is
+// the smallest one, which is what this returns, in float64.
+__device__ __forceinline__ double min_eig_sym3(double xx, double xy, double xz, double yy, double yz, double zz) {
+    const double q = (xx + yy + zz) * (1.0 / 3.0);
+    const double a = xx - q, b = yy - q, c = zz - q;
+    const double p1 = xy * xy + xz * xz + yz * yz;
+    const double p2 = a * a + b * b + c * c + 2.0 * p1;
+    if (!(p2 > 0.0)) return q;  // scalar matrix (incl. all-zero): every eigenvalue is q
+    const double p = sqrt(p2 * (1.0 / 6.0));
+    const double ip = 1.0 / p;
+    const double ba = a * ip, bb = b * ip, bc = c * ip, bxy = xy * ip, bxz = xz * ip, byz = yz * ip;
+    double r = 0.5 * (ba * (bb * bc - byz * byz) - bxy * (bxy * bc - byz * bxz) + bxz * (bxy * byz - bb * bxz));
+    r = fmin(1.0, fmax(-1.0, r));
+    const double phi = acos(r) * (1.0 / 3.0);
+    // eigenvalues: q + 2p cos(phi + 2k pi/3); k = 1 gives the smallest
+    return q + 2.0 * p * cos(phi + 2.0943951023931954923);
+}
+
+// EXACT = true reproduces NumPy's evaluation order with individually rounded operations
+// (no FMA contraction), so that given bit-identical window sums the flow is bit-identical.
+template <bool EXACT>
+__device__ __forceinline__ Flow3 solve3(double xx, double xy, double xz, double yy, double yz, double zz,
+                                        double tx, double ty, double tz) {
+    Flow3 o;
+    if (EXACT) {
+#define M(a, b) __dmul_rn(a, b)
+#define A(a, b) __dadd_rn(a, b)
+#define S(a, b) __dsub_rn(a, b)
+        double det = M(M(xx, yy), zz);
+        det = A(det, M(M(M(2.0, xy), xz), yz));
+        det = S(det, M(yy, M(xz, xz)));
+        det = S(det, M(zz, M(xy, xy)));
+        det = S(det, M(xx, M(yz, yz)));
+        const double ninv = -__drcp_rn(A(det, kEps));
+        o.vx = M(ninv, A(A(M(S(M(yy, zz), M(yz, yz)), tx), M(S(M(xz, yz), M(xy, zz)), ty)), M(S(M(xy, yz), M(xz, yy)), tz)));
+        o.vy = M(ninv, A(A(M(S(M(yz, xz), M(xy, zz)), tx), M(S(M(xx, zz), M(xz, xz)), ty)), M(S(M(xz, xy), M(xx, yz)), tz)));
+        o.vz = M(ninv, A(A(M(S(M(xy, yz), M(yy, xz)), tx), M(S(M(xy, xz), M(xx, yz)), ty)), M(S(M(xx, yy), M(xy, xy)), tz)));
+#undef M
+#undef A
+#undef S
+    } else {
+        const double cxx = yy * zz - yz * yz, cxy = xz * yz - xy * zz, cxz = xy * yz - xz * yy;
+        const double cyy = xx * zz - xz * xz, cyz = xz * xy - xx * yz, czz = xx * yy - xy * xy;
+        // Sarrus determinant written exactly as the reference does (cofactor expansion would
+        // round differently where the tensor is near-singular)
+        const double det = xx * yy * zz + 2.0 * xy * xz * yz - yy * xz * xz - zz * xy * xy - xx * yz * yz;
+        const double ninv = -1.0 / (det + kEps);
+        o.vx = ninv * (cxx * tx + cxy * ty + cxz * tz);
+        o.vy = ninv * (cxy * tx + cyy * ty + cyz * tz);
+        o.vz = ninv * (cxz * tx + cyz * ty + czz * tz);
+    }
+    o.rel = min_eig_sym3(xx, xy, xz, yy, yz, zz);
+    return o;
+}
+
+// 2D: the discriminant is evaluated with individually rounded operations in both modes so
+// that its sign (NaN vs tiny real, calc_flow.py:166) follows NumPy's.
+template <bool EXACT>
+__device__ __forceinline__ Flow2 solve2(double xx, double xy, double yy, double tx, double ty) {
+    Flow2 o;
+    const double det = __dsub_rn(__dmul_rn(xx, yy), __dmul_rn(xy, xy));
+    const double inv = __drcp_rn(__dadd_rn(det, kEps));
+    o.vx = __dmul_rn(inv, __dadd_rn(__dmul_rn(yy, -tx), __dmul_rn(-xy, -ty)));
+    o.vy = __dmul_rn(inv, __dadd_rn(__dmul_rn(-xy, -tx), __dmul_rn(xx, -ty)));
+    const double tr = __dadd_rn(xx, yy);
+    const double disc = __dsub_rn(__dmul_rn(tr, tr), __dmul_rn(4.0, det));
+    const double root = sqrt(disc);  // NaN when disc rounds negative, like np.sqrt
+    const double l1 = __dmul_rn(__dadd_rn(tr, root), 0.5);
+    const double l2 = __dmul_rn(__dsub_rn(tr, root), 0.5);
+    o.rel = (l1 != l1 || l2 != l2) ? (l1 + l2) : fmin(l1, l2);  // np.minimum propagates NaN
+    return o;
+}
+
+}  // namespace of3d

@@ -1,0 +1,244 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI,
+against (1) the reference's golden vectors, (2) the CPU oracle on seeded inputs.
+
+Tolerances:
+  fp64 exact mode : flow bit-identical to the reference.
+  fp64            : max|dv| <= 1e-9*max|v_ref| everywhere and |dv| <= 1e-9*|v_ref| where rel_ref > median;
+                    3D rel within 8*eps32*lambda_max of the reference's float32 value and within
+                    1e-10*lambda_max of the float64 oracle; 2D rel 1e-9 relative.
+  fp32            : |dv| <= 1e-4*max|v_ref| where rel_ref > median (north_star's stated tolerance).
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_2D, GOLDEN_3D, load_golden
+from oracle import lk_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+EPS32 = float(np.finfo(np.float32).eps)
+
+
+def _cf():
+    from opticalflow3d_dev_b200 import calc_flow
+    return calc_flow
+
+
+def assert_flow_close(got, ref, rel_ref, rtol, name):
+    vmax = max(float(np.max(np.abs(r))) for r in ref)
+    mask = rel_ref > np.nanmedian(rel_ref)
+    for g, r, c in zip(got, ref, 'xyz'):
+        g = np.asarray(g, dtype=np.float64)
+        d = np.abs(g - r)
+        assert np.all(np.isfinite(g)), '%s v%s not finite' % (name, c)
+        assert d.max() <= rtol * vmax, '%s v%s max abs err %.3e (vmax %.3e)' % (name, c, d.max(), vmax)
+        bad = d[mask] > rtol * np.maximum(np.abs(r[mask]), 1e-3 * vmax)
+        assert not bad.any(), '%s v%s elementwise: %d voxels' % (name, c, int(bad.sum()))
+
+
+def lam_max_bound(img, sig, ndim):
+    if ndim == 3:
+        it = orc.lk_flow3d(img, *sig, return_intermediates=True)[-1]
+        return np.abs(it['wdx2']) + np.abs(it['wdy2']) + np.abs(it['wdz2'])
+    it = orc.lk_flow2d(img, *sig, return_intermediates=True)[-1]
+    return np.abs(it['wdx2']) + np.abs(it['wdy2'])
+
+
+# ------------------------------------------------------------------ golden vectors (reference outputs)
+@pytest.mark.parametrize('name', GOLDEN_3D)
+def test_golden_3d_exact_mode_bit_identical(name):
+    g = load_golden(name)
+    vx, vy, vz, rel = _cf().calc_flow3D(g['images'], *g['sigmas'], exact=True)
+    assert vx.dtype == np.float64 and rel.dtype == np.float32 and vx.shape == g['vx'].shape
+    assert np.array_equal(vx, g['vx']) and np.array_equal(vy, g['vy']) and np.array_equal(vz, g['vz'])
+    lam = lam_max_bound(g['images'], g['sigmas'], 3)
+    assert np.all(np.abs(rel.astype(np.float64) - g['rel']) <= 8 * EPS32 * lam)
+
+
+@pytest.mark.parametrize('name', GOLDEN_2D)
+def test_golden_2d_exact_mode_bit_identical(name):
+    g = load_golden(name)
+    vx, vy, rel = _cf().calc_flow2D(g['images'], *g['sigmas'], exact=True)
+    assert np.array_equal(vx, g['vx']) and np.array_equal(vy, g['vy'])
+    assert np.array_equal(rel, g['rel'], equal_nan=True)
+
+
+@pytest.mark.parametrize('generic', [False, True])
+@pytest.mark.parametrize('name', GOLDEN_3D)
+def test_golden_3d_fp64(name, generic):
+    g = load_golden(name)
+    vx, vy, vz, rel = _cf().calc_flow3D(g['images'], *g['sigmas'], generic=generic, rel_dtype='float64')
+    assert_flow_close((vx, vy, vz), (g['vx'], g['vy'], g['vz']), g['rel'], 1e-9, name)
+    lam = lam_max_bound(g['images'], g['sigmas'], 3)
+    assert np.all(np.abs(rel - g['rel']) <= 8 * EPS32 * lam)
+    rel64 = orc.lk_flow3d(g['images'], *g['sigmas'], rel_mode='float64')[3]
+    assert np.all(np.abs(rel - rel64) <= 1e-10 * lam)
+
+
+@pytest.mark.parametrize('generic', [False, True])
+@pytest.mark.parametrize('name', GOLDEN_2D)
+def test_golden_2d_fp64(name, generic):
+    g = load_golden(name)
+    vx, vy, rel = _cf().calc_flow2D(g['images'], *g['sigmas'], generic=generic)
+    assert_flow_close((vx, vy), (g['vx'], g['vy']), g['rel'], 1e-9, name)
+    lam = lam_max_bound(g['images'], g['sigmas'], 2)
+    ok = np.isfinite(g['rel'])
+    assert np.all(np.abs(rel[ok] - g['rel'][ok]) <= 1e-9 * lam[ok])
+
+
+@pytest.mark.parametrize('name', GOLDEN_3D + GOLDEN_2D)
+def test_golden_fp32_mode(name):
+    g = load_golden(name)
+    if g['images'].ndim == 4:
+        out = _cf().calc_flow3D(g['images'], *g['sigmas'], precision='fp32')
+        ref = (g['vx'], g['vy'], g['vz'])
+    else:
+        out = _cf().calc_flow2D(g['images'], *g['sigmas'], precision='fp32')
+        ref = (g['vx'], g['vy'])
+    assert all(o.dtype == np.float32 for o in out)
+    vmax = max(float(np.abs(r).max()) for r in ref)
+    mask = g['rel'] > np.nanmedian(g['rel'])
+    for o, r in zip(out[:-1], ref):
+        assert np.abs(o.astype(np.float64) - r)[mask].max() <= 1e-4 * vmax
+    lam = lam_max_bound(g['images'], g['sigmas'], g['images'].ndim - 1)
+    ok = np.isfinite(g['rel'])
+    assert np.all(np.abs(out[-1].astype(np.float64) - g['rel'])[ok] <= 1e-4 * lam[ok])
+
+
+# ------------------------------------------------------------------ oracle on fresh seeded inputs
+@pytest.mark.parametrize('shape,sig,dtype', [
+    ((7, 24, 70, 100), (3, 1, 4), np.uint16),       # BASELINE cfg4 parameters, cropped
+    ((7, 32, 64, 64), (1, 1, 4), np.uint16),        # BASELINE cfg1 parameters, cropped
+    ((13, 20, 50, 60), (3, 2, 6), np.uint16),       # cfg3 parameters
+    ((19, 6, 20, 130), (3, 3, 8), np.float32),      # cfg5 parameters; window wider than z and y
+    ((7, 3, 5, 4), (1, 1, 4), np.uint8),            # volume smaller than every filter
+    ((7, 1, 40, 33), (2, 1, 3), np.float64),        # single z plane through the 3D entry point
+    ((5, 9, 31, 37), (0.7, 0.5, 1.2), np.int16),    # sub-pixel sigmas: 3-tap S, 5-tap T
+])
+def test_oracle_3d_fp64(shape, sig, dtype):
+    from opticalflow3d_dev_b200.synth import make_stack
+    kw = dict(amp=(20, 120), noise=3.0) if dtype == np.uint8 else {}
+    img = make_stack(shape, seed=sum(shape), dtype=dtype, **kw)
+    ref = orc.lk_flow3d(img, *sig, rel_mode='float64', return_intermediates=True)
+    vx, vy, vz, rel = _cf().calc_flow3D(img, *sig, rel_dtype='float64')
+    it = ref[4]
+    lam = np.abs(it['wdx2']) + np.abs(it['wdy2']) + np.abs(it['wdz2'])
+    if shape[1] > 1:
+        assert_flow_close((vx, vy, vz), ref[:3], ref[3], 1e-9, str(shape))
+    else:
+        # One z plane: dI/dz cancels to exactly 0 in the reference's paired summation, the tensor is
+        # singular and the reference returns 0/eps = 0 everywhere.  Only the exact mode (below) is
+        # comparable on a singular tensor; the default mode must stay finite.
+        assert all(np.all(np.isfinite(v)) for v in (vx, vy, vz))
+    assert np.all(np.abs(rel - ref[3]) <= 1e-10 * lam)
+    ex = _cf().calc_flow3D(img, *sig, exact=True, rel_dtype='float64')
+    assert all(np.array_equal(a, b) for a, b in zip(ex[:3], ref[:3]))
+
+
+@pytest.mark.parametrize('shape,sig,dtype', [
+    ((7, 300, 260), (1.5, 1, 4), np.uint16),        # BASELINE cfg2 parameters, cropped
+    ((7, 64, 1100), (3, 1, 4), np.uint16),
+    ((13, 9, 7), (3, 2, 6), np.float32),            # frame smaller than the filters
+    ((19, 100, 90), (2, 3, 8), np.uint8),
+])
+def test_oracle_2d_fp64(shape, sig, dtype):
+    from opticalflow3d_dev_b200.synth import make_stack
+    kw = dict(amp=(20, 120), noise=3.0) if dtype == np.uint8 else {}
+    img = make_stack(shape, seed=sum(shape), dtype=dtype, **kw)
+    ref = orc.lk_flow2d(img, *sig, return_intermediates=True)
+    vx, vy, rel = _cf().calc_flow2D(img, *sig)
+    assert_flow_close((vx, vy), ref[:2], ref[2], 1e-9, str(shape))
+    lam = np.abs(ref[3]['wdx2']) + np.abs(ref[3]['wdy2'])
+    ok = np.isfinite(ref[2])
+    assert np.all(np.abs(rel - ref[2])[ok] <= 1e-9 * lam[ok])
+    ex = _cf().calc_flow2D(img, *sig, exact=True)
+    assert np.array_equal(ex[0], ref[0]) and np.array_equal(ex[1], ref[1])
+    assert np.array_equal(ex[2], ref[2], equal_nan=True)
+
+
+# ------------------------------------------------------------------ behaviour at the boundary
+def test_input_not_mutated_noncontiguous_and_extra_frames():
+    from opticalflow3d_dev_b200.synth import make_stack
+    big = make_stack((11, 10, 40, 50), seed=3, dtype=np.uint16)
+    view = big[:, ::2, :, ::-1]                       # non-contiguous, negative stride
+    keep = big.copy()
+    a = _cf().calc_flow3D(view, 1, 1, 2)
+    assert np.array_equal(big, keep)
+    b = _cf().calc_flow3D(np.ascontiguousarray(view), 1, 1, 2)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # Nt = 11 window vs its central 7 frames: identical (only frames within ceil(3 tSig) matter)
+    c = _cf().calc_flow3D(np.ascontiguousarray(view[2:9]), 1, 1, 2)
+    assert all(np.array_equal(x, y) for x, y in zip(a, c))
+
+
+def test_constant_image_gives_exact_zeros():
+    for prec in ('fp64', 'fp32'):
+        out = _cf().calc_flow3D(np.full((7, 6, 20, 24), 37, dtype=np.uint16), 1, 1, 2, precision=prec)
+        assert all(not np.any(o) for o in out), prec
+        out = _cf().calc_flow2D(np.full((7, 20, 24), 5.5, dtype=np.float32), 1, 1, 2, precision=prec)
+        assert all(not np.any(o) for o in out), prec
+
+
+def test_cuda_tensor_in_cuda_tensor_out():
+    import torch
+    g = load_golden('g3_a')
+    t = torch.from_numpy(g['images'].astype(np.int16)).cuda()   # torch has no uint16 arithmetic; int16 holds the data
+    assert np.array_equal(t.cpu().numpy(), g['images'])
+    vx, vy, vz, rel = _cf().calc_flow3D(t, *g['sigmas'], exact=True)
+    assert vx.is_cuda and rel.dtype == torch.float32
+    assert np.array_equal(vx.cpu().numpy(), g['vx']) and np.array_equal(vz.cpu().numpy(), g['vz'])
+
+
+def test_frames_entry_point_matches_contiguous():
+    import ctypes as C
+    import torch
+    from opticalflow3d_dev_b200 import _lib
+    from opticalflow3d_dev_b200.taps import flow_taps
+    g = load_golden('g3_g')                                     # Nt = 9 > 7 taps
+    img = g['images']
+    ref = _cf().calc_flow3D(img, *g['sigmas'], rel_dtype='float64')
+    ctx = _lib.get_context(0)
+    taps, keep = _lib.make_taps(flow_taps(*g['sigmas']))
+    frames = [torch.from_numpy(img[k].astype(np.int16)).cuda() for k in range(1, 8)]   # scattered allocations
+    ptrs = (C.c_void_p * 7)(*[f.data_ptr() for f in frames])
+    outs = [torch.empty(img.shape[1:], dtype=torch.float64, device='cuda') for _ in range(4)]
+    torch.cuda.synchronize()
+    rc = ctx.lib.of3d_flow_frames(ctx.handle, 3, ptrs, _lib.I16, _lib.DEVICE, *img.shape[1:], C.byref(taps), _lib.FP64, 0,
+                                  *[C.c_void_p(o.data_ptr()) for o in outs], _lib.DEVICE)
+    _lib.check(rc, 'of3d_flow_frames')
+    assert all(np.array_equal(o.cpu().numpy(), r) for o, r in zip(outs, ref))
+
+
+def test_bad_arguments_return_errors_not_crashes():
+    import ctypes as C
+    from opticalflow3d_dev_b200 import _lib
+    from opticalflow3d_dev_b200.taps import flow_taps
+    ctx = _lib.get_context(0)
+    taps, keep = _lib.make_taps(flow_taps(1, 1, 2))
+    img = np.zeros((6, 4, 8, 8), dtype=np.uint16)
+    out = [np.zeros((4, 8, 8)) for _ in range(4)]
+    p = [C.c_void_p(o.ctypes.data) for o in out]
+    rc = ctx.lib.of3d_flow3d(ctx.handle, C.c_void_p(img.ctypes.data), _lib.U16, _lib.HOST, 6, 4, 8, 8, C.byref(taps),
+                             _lib.FP64, 0, *p, _lib.HOST)
+    assert rc == -1 and 'odd' in _lib.last_error()
+    rc = ctx.lib.of3d_flow3d(ctx.handle, C.c_void_p(img.ctypes.data), 99, _lib.HOST, 7, 4, 8, 8, C.byref(taps),
+                             _lib.FP64, 0, *p, _lib.HOST)
+    assert rc == -1
+    rc = ctx.lib.of3d_flow3d(ctx.handle, None, _lib.U16, _lib.HOST, 7, 4, 8, 8, C.byref(taps), _lib.FP64, 0, *p, _lib.HOST)
+    assert rc == -1
+
+
+def test_synth_blobs_kernel_statistics():
+    import torch
+    from opticalflow3d_dev_b200 import _lib
+    ctx = _lib.get_context(0)
+    buf = torch.empty((3, 16, 64, 96), dtype=torch.int16, device='cuda')
+    torch.cuda.synchronize()
+    _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, buf.data_ptr(), 3, 16, 64, 96, 10, 0, 1234), 'synth')
+    a = buf.cpu().numpy().view(np.uint16).astype(np.float64)
+    assert 90 < np.median(a) < 130 and a.max() > 300 and a.min() >= 60
+    # shard-consistency: generating frame 11 alone equals frame index 1 of the (t0=10) block
+    one = torch.empty((1, 16, 64, 96), dtype=torch.int16, device='cuda')
+    torch.cuda.synchronize()
+    _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, one.data_ptr(), 1, 16, 64, 96, 11, 0, 1234), 'synth')
+    assert np.array_equal(one.cpu().numpy()[0], buf.cpu().numpy()[1])
