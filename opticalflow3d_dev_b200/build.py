@@ -14,9 +14,9 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'libof3d.so')
-SOURCES = ['of3d.cu']
+SOURCES = ['of3d.cu', 'fast_f64.cu', 'fast_f32.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '-shared',
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
               '--expt-relaxed-constexpr', '-Xptxas', '-v']
 
 
@@ -38,17 +38,33 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB + '.tmp']
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(PKG, 'build')
+    os.makedirs(objdir, exist_ok=True)
     log = os.path.join(PKG, 'build.log')
+    # one object per translation unit, compiled concurrently (the marching kernels are heavily unrolled)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace('.cu', '.o'))
+        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    text, failed = '', False
+    for cmd, obj, p in procs:
+        out = p.communicate()[0]
+        text += ' '.join(cmd) + '\n' + out
+        failed |= p.returncode != 0
+    if not failed:
+        cmd = [nvcc, '-shared', '-o', LIB + '.tmp'] + [obj for _, obj, _ in procs]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        text += ' '.join(cmd) + '\n' + res.stdout + res.stderr
+        failed = res.returncode != 0
     with open(log, 'w') as fh:
-        fh.write(' '.join(cmd) + '\n' + res.stdout + res.stderr)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+        fh.write(text)
+    if failed:
+        sys.stderr.write(text[-8000:])
         raise RuntimeError('nvcc failed (see %s)' % log)
     os.replace(LIB + '.tmp', LIB)
     if verbose:
-        print(res.stderr)
+        print(text)
     return LIB
 
 

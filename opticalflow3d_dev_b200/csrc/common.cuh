@@ -39,5 +39,60 @@ const char* cuda_err_name(cudaError_t e);
     } while (0)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a = 512) { return (x + a - 1) / a * a; }
+
+struct Shape {
+    int ndim;            // 2 or 3
+    int64_t nz, ny, nx;  // nz == 1 for 2D
+    int64_t n() const { return nz * ny * nx; }
+};
+
+}  // namespace of3d
+
+// The opaque context of the C ABI.
+struct of3d_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char* ws = nullptr;   // device workspace
+    size_t ws_cap = 0;
+    size_t ws_off = 0;    // bump pointer (reset every call)
+    int async = 0;
+    int64_t launches = 0;
+    int sm_count = 148;
+};
+
+namespace of3d {
+
+template <typename P>
+static inline P* ws_take(of3d_ctx* c, size_t count) {
+    P* p = reinterpret_cast<P*>(c->ws + c->ws_off);
+    c->ws_off += align_up(count * sizeof(P));
+    return p;
+}
+
+// Marching-kernel pipeline (pipeline_fast.cuh): returns OF3D_OK, an error, or kNotSupported when the
+// tap counts have no specialised instantiation (the caller then runs the generic pipeline).
+constexpr int kNotSupported = 1;
+template <typename T>
+int run_fast(of3d_ctx* c, const Shape& s, const T* ic, const T* dt0, const of3d_taps* t, T* vx, T* vy, T* vz, T* rel);
+
+// Tap-count classes with a specialised marching instantiation (shorter filters are zero-padded to the class)
+static inline int spatial_class(const of3d_taps* t) {
+    const int kr = t->nD > t->nG ? t->nD : t->nG, ks = t->nS;
+    if (kr <= 7 && ks <= 3) return 0;
+    if (kr <= 13 && ks <= 5) return 1;
+    if (kr <= 19 && ks <= 7) return 2;
+    if (kr <= 25 && ks <= 7) return 3;
+    return -1;
+}
+static inline int window_class(const of3d_taps* t) {
+    const int ks[6] = {7, 13, 19, 25, 37, 49};
+    for (int i = 0; i < 6; ++i)
+        if (t->nW <= ks[i]) return i;
+    return -1;
+}
+static inline bool fast_supported(const of3d_taps* t) { return spatial_class(t) >= 0 && window_class(t) >= 0; }
+// workspace volumes of compute type used by run_fast (excluding ic and dt0)
+static inline int fast_volumes(int ndim) { return ndim == 3 ? 9 + 4 + 9 : 3 + 3 + 5; }
 
 }  // namespace of3d

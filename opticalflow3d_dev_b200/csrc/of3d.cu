@@ -22,17 +22,6 @@ void set_error(const std::string& msg) { g_err = msg; }
 
 using namespace of3d;
 
-struct of3d_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    char* ws = nullptr;       // device workspace
-    size_t ws_cap = 0;
-    size_t ws_off = 0;        // bump pointer (reset every call)
-    int async = 0;
-    int64_t launches = 0;
-    int sm_count = 148;
-};
-
 namespace of3d {
 
 static size_t dtype_size(int dt) {
@@ -44,8 +33,6 @@ static size_t dtype_size(int dt) {
         default: return 0;
     }
 }
-
-static inline size_t align_up(size_t x, size_t a = 512) { return (x + a - 1) / a * a; }
 
 // Scipy's symmetry test (ni_filters.c): odd length and |w[r+i] -/+ w[r-i]| <= DBL_EPSILON
 static int tap_symmetry(const double* w, int n) {
@@ -67,12 +54,6 @@ static Filt<T> make_filt(const double* w, int n) {
     for (int i = 0; i < kMaxTaps; ++i) f.w[i] = i < n ? (T)w[i] : T(0);  // rounded once to the compute type
     return f;
 }
-
-struct Shape {
-    int ndim;           // 2 or 3
-    int64_t nz, ny, nx; // nz == 1 for 2D
-    int64_t n() const { return nz * ny * nx; }
-};
 
 static int grid_for(const of3d_ctx* c, int64_t n, int block = 256) {
     int64_t g = ceil_div(n, block);
@@ -96,21 +77,13 @@ static int ws_ensure(of3d_ctx* c, size_t bytes) {
     return OF3D_OK;
 }
 
-template <typename P>
-static P* ws_take(of3d_ctx* c, size_t count) {
-    size_t bytes = align_up(count * sizeof(P));
-    P* p = reinterpret_cast<P*>(c->ws + c->ws_off);
-    c->ws_off += bytes;
-    return p;
-}
-
 // Volumes of compute type needed by the generic pipeline (see run_generic)
 static int generic_volumes(int ndim) { return ndim == 3 ? 2 + 2 + 4 + 1 + 9 : 2 + 2 + 3 + 1 + 5; }
 
 static size_t plan_bytes(int ndim, int64_t kt, int64_t n, int in_dtype, int precision, int in_mem, int out_mem) {
     const size_t ts = precision == OF3D_FP32 ? 4 : 8;
     size_t b = 0;
-    b += (size_t)generic_volumes(ndim) * align_up((size_t)n * ts);
+    b += (size_t)std::max(generic_volumes(ndim), 2 + fast_volumes(ndim)) * align_up((size_t)n * ts);
     if (in_mem == OF3D_HOST) b += (size_t)kt * align_up((size_t)n * dtype_size(in_dtype));
     if (out_mem == OF3D_HOST) b += (size_t)(ndim + 1) * align_up((size_t)n * ts);
     return b + 4096;
@@ -144,6 +117,20 @@ struct GenericPipe {
         c->launches++;
     }
 
+    int run_temporal(const FramePtrs& fp, int in_dtype, T* ic, T* dt0) {
+        switch (in_dtype) {
+            case OF3D_U8: temporal<uint8_t>(fp, ic, dt0); break;
+            case OF3D_U16: temporal<uint16_t>(fp, ic, dt0); break;
+            case OF3D_I16: temporal<int16_t>(fp, ic, dt0); break;
+            case OF3D_F32: temporal<float>(fp, ic, dt0); break;
+            case OF3D_F64: temporal<double>(fp, ic, dt0); break;
+            case OF3D_I32: temporal<int32_t>(fp, ic, dt0); break;
+            case OF3D_U32: temporal<uint32_t>(fp, ic, dt0); break;
+            default: set_error("unsupported input dtype"); return OF3D_ERR_ARG;
+        }
+        return OF3D_OK;
+    }
+
     int run(const FramePtrs& fp, int in_dtype, T* vx, T* vy, T* vz, T* rel) {
         const int64_t n = s.n();
         T* ic = ws_take<T>(c, n);
@@ -157,16 +144,7 @@ struct GenericPipe {
         T* prod = ws_take<T>(c, n);
         const int nch = s.ndim == 3 ? 9 : 5;
         T* w = ws_take<T>(c, (size_t)nch * n);
-        switch (in_dtype) {
-            case OF3D_U8: temporal<uint8_t>(fp, ic, dt0); break;
-            case OF3D_U16: temporal<uint16_t>(fp, ic, dt0); break;
-            case OF3D_I16: temporal<int16_t>(fp, ic, dt0); break;
-            case OF3D_F32: temporal<float>(fp, ic, dt0); break;
-            case OF3D_F64: temporal<double>(fp, ic, dt0); break;
-            case OF3D_I32: temporal<int32_t>(fp, ic, dt0); break;
-            case OF3D_U32: temporal<uint32_t>(fp, ic, dt0); break;
-            default: set_error("unsupported input dtype"); return OF3D_ERR_ARG;
-        }
+        if (int rc = run_temporal(fp, in_dtype, ic, dt0)) return rc;
         chain(dt0, dt, t1, t2, fG, fG, fG);          // calc_flow.py:279 / 116
         chain(ic, dy, t1, t2, fD, fS, fS);           // :282 / 119
         chain(ic, dx, t1, t2, fS, fD, fS);           // :285 / 122
@@ -217,6 +195,15 @@ static int run_typed(of3d_ctx* c, const Shape& s, const FramePtrs& fp, int in_dt
     }
     GenericPipe<T, false> g{c, s, make_filt<T>(t->D, t->nD), make_filt<T>(t->S, t->nS), make_filt<T>(t->G, t->nG),
                             make_filt<T>(t->T, t->nT), make_filt<T>(t->W, t->nW)};
+    if (!(flags & OF3D_FLAG_GENERIC) && fast_supported(t)) {
+        // marching-kernel pipeline: temporal derivative (elementwise), then kernels_march.cuh
+        T* ic = ws_take<T>(c, s.n());
+        T* dt0 = ws_take<T>(c, s.n());
+        if (int rc = g.run_temporal(fp, in_dtype, ic, dt0)) return rc;
+        const int rc = run_fast<T>(c, s, ic, dt0, t, vx, vy, vz, rel);
+        if (rc != kNotSupported) return rc;
+        c->ws_off -= 2 * align_up((size_t)s.n() * sizeof(T));
+    }
     return g.run(fp, in_dtype, vx, vy, vz, rel);
 }
 

@@ -13,24 +13,54 @@ constexpr double kEps = 2.220446049250313e-16;  // np.finfo(float).eps, calc_flo
 struct Flow3 { double vx, vy, vz, rel; };
 struct Flow2 { double vx, vy, rel; };
 
-// Smallest eigenvalue of [[xx,xy,xz],[xy,yy,yz],[xz,yz,zz]]: trigonometric closed form
-// (Smith 1961).  The reference runs LAPACK cgeev on complex64 (float32 accuracy); for a
-// real symmetric matrix the eigenvalues are real and the lexicographic complex minimum is
-// the smallest one, which is what this returns, in float64.
+// Smallest eigenvalue of the symmetric matrix [[xx,xy,xz],[xy,yy,yz],[xz,yz,zz]].
+// The reference runs LAPACK cgeev on complex64 (float32 accuracy); for a real symmetric matrix the
+// eigenvalues are real and the lexicographic complex minimum is the smallest one, which is what this
+// returns, in float64.
+//
+// Closed form (Smith 1961): with q = tr/3, p = sqrt(|A - qI|_F^2 / 6), B = (A - qI)/p, r = det(B)/2,
+// the eigenvalues are q + 2p*t where t runs over the roots of the Chebyshev cubic 4t^3 - 3t = r; the
+// smallest is t = cos(acos(r)/3 + 2pi/3) in [-1, -1/2].  fp64 acos/cos cost ~100 FP64-pipe instructions,
+// so the root is found instead on the shifted cubic: with s = t + 1/2 in [-1/2, 0] and e = 1 - r in [0, 2],
+//     s^2 (4s - 6) + e = 0 .
+// The seed is the fp32 fixed-point iterate of s = -sqrt(e / (6 - 4s)) (contraction rate < 0.19, exact as
+// e -> 0), polished by Newton steps in fp64 whose slope reciprocal only needs fp32 accuracy because Newton
+// is self-correcting.  In this form the convergence is quadratic in the RELATIVE error of s, also next to the
+// double root (two equal smallest eigenvalues, e -> 0) where the trigonometric form loses half the digits.
 __device__ __forceinline__ double min_eig_sym3(double xx, double xy, double xz, double yy, double yz, double zz) {
     const double q = (xx + yy + zz) * (1.0 / 3.0);
     const double a = xx - q, b = yy - q, c = zz - q;
     const double p1 = xy * xy + xz * xz + yz * yz;
-    const double p2 = a * a + b * b + c * c + 2.0 * p1;
+    const double p2 = (a * a + b * b + c * c + 2.0 * p1) * (1.0 / 6.0);
     if (!(p2 > 0.0)) return q;  // scalar matrix (incl. all-zero): every eigenvalue is q
-    const double p = sqrt(p2 * (1.0 / 6.0));
-    const double ip = 1.0 / p;
+    // ip = 1/sqrt(p2): fp32 seed + two fp64 Newton steps; library path when p2 leaves the float range
+    double ip = (double)rsqrtf((float)p2);
+    if (!(ip > 0.0) || ip > 1e30) ip = rsqrt(p2);
+    else {
+        ip = ip * (1.5 - 0.5 * p2 * ip * ip);
+        ip = ip * (1.5 - 0.5 * p2 * ip * ip);
+    }
+    const double p = p2 * ip;
     const double ba = a * ip, bb = b * ip, bc = c * ip, bxy = xy * ip, bxz = xz * ip, byz = yz * ip;
     double r = 0.5 * (ba * (bb * bc - byz * byz) - bxy * (bxy * bc - byz * bxz) + bxz * (bxy * byz - bb * bxz));
     r = fmin(1.0, fmax(-1.0, r));
-    const double phi = acos(r) * (1.0 / 3.0);
-    // eigenvalues: q + 2p cos(phi + 2k pi/3); k = 1 gives the smallest
-    return q + 2.0 * p * cos(phi + 2.0943951023931954923);
+    const double e = 1.0 - r;
+    const float ef = (float)e;
+    double s = 0.0;
+    if (ef > 0.0f) {
+        float sf = -sqrtf(ef * (1.0f / 6.0f));
+#pragma unroll
+        for (int it = 0; it < 4; ++it) sf = -sqrtf(__fdividef(ef, 6.0f - 4.0f * sf));
+        s = (double)sf;
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const double f = s * s * (4.0 * s - 6.0) + e;
+            const double fp = 12.0 * s * (s - 1.0);            // > 0 for s < 0
+            s -= f * (double)__frcp_rn((float)fp);
+        }
+        s = fmin(0.0, fmax(-0.5, s));
+    }
+    return (q - p) + 2.0 * p * s;
 }
 
 // EXACT = true reproduces NumPy's evaluation order with individually rounded operations
