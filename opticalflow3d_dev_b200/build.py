@@ -45,7 +45,7 @@ def build_library(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace('.cu', '.o'))
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get('OF3D_NVCC_EXTRA', '').split() + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     text, failed = '', False
     for cmd, obj, p in procs:

@@ -199,33 +199,40 @@ __global__ void __launch_bounds__(WPB * 32) march_window(const WindowArgs<T, K> 
     T* outc = a.out + (int64_t)ch * g.vol;
     T* tile = sm + WPB * Pre::elems_per_warp + warp * (P * 33) + lane;   // this lane's column of the P-row tile
 
+    // The march is padded to whole unroll periods and runs without any branch in the unrolled body: steps
+    // before the first complete output (s < 2R) and after the last (s >= nout + 2R) compute as usual on clamped
+    // inputs and are masked at the store (one unsigned compare also covers out-of-range lanes).
     const int nout = c1 - c0;
-    const int nsteps = nout + 2 * R;          // inputs c0-R .. c1-1+R
+    const unsigned nvalid = lane_ok ? (unsigned)nout : 0u;
+    const int nsteps = (nout + 2 * R + P - 1) / P * P;
 #pragma unroll
     for (int d = 0; d < DEPTH - 1; ++d) pre.issue(d);
 
     T acc[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) acc[i] = T(0);
-    char* optr = reinterpret_cast<char*>(outc + base + (int64_t)c0 * g.stride_march);   // plain store position
+    // plain store position of the output completed at step s: c0 + s - 2R
+    char* optr = reinterpret_cast<char*>(outc + base) + ((int64_t)c0 - 2 * R) * pre.stride_bytes;
 
+    // The value of step s+1 is read from the ring while step s is being accumulated (software pipelining:
+    // the LDS latency hides under the K FMAs of the current step).
+    cp_async_wait<DEPTH - 2>();
+    T vn0 = pre.read(0, 0), vn1 = PROD ? pre.read(0, 1) : T(1);
 #pragma unroll 1
     for (int s0 = 0; s0 < nsteps; s0 += P) {
 #pragma unroll
         for (int ph = 0; ph < P; ++ph) {
-            const int s = s0 + ph;
-            if (s < nsteps) {
-                pre.issue((ph + DEPTH - 1) % DEPTH);
-                cp_async_wait<DEPTH - 1>();
-                T v = pre.read(ph % DEPTH, 0);
-                if (PROD) v *= pre.read(ph % DEPTH, 1);
-                const T res = ring_push<T, K, P>(acc, a.f, v, ph);
-                if (TR) {
-                    tile[ph * 33] = res;                // output index s - 2R (may be < 0 during warm-up)
-                } else if (s >= 2 * R) {                // output c0 + (s - 2R) is complete
-                    if (lane_ok) *reinterpret_cast<T*>(optr) = res;
-                    optr += pre.stride_bytes;
-                }
+            const T v = PROD ? vn0 * vn1 : vn0;
+            pre.issue((ph + DEPTH - 1) % DEPTH);
+            cp_async_wait<DEPTH - 2>();            // step s+1 has landed
+            vn0 = pre.read((ph + 1) % DEPTH, 0);
+            if (PROD) vn1 = pre.read((ph + 1) % DEPTH, 1);
+            const T res = ring_push<T, K, P>(acc, a.f, v, ph);
+            if (TR) {
+                tile[ph * 33] = res;                // output index s - 2R; validity is checked at the flush
+            } else {
+                if ((unsigned)(s0 + ph - 2 * R) < nvalid) *reinterpret_cast<T*>(optr) = res;
+                optr += pre.stride_bytes;
             }
         }
         if (TR) tile_flush<T, P>(tile - lane, outc + other * g.stride_other, g.n_march, c0, s0 - 2 * R, nout, lane0, g.n_lane);
@@ -297,7 +304,8 @@ __global__ void __launch_bounds__(WPB * 32) march_grad(const GradArgs<T, KR, KS>
     T* tiles = sm + WPB * Pre::elems_per_warp + warp * (NOUT * P * 33);   // NOUT tiles of P rows
 
     const int nout = c1 - c0;
-    const int nsteps = nout + 2 * R;
+    const unsigned nvalid = lane_ok ? (unsigned)nout : 0u;
+    const int nsteps = (nout + 2 * R + P - 1) / P * P;     // padded to whole periods: no branch in the unrolled body
 #pragma unroll
     for (int d = 0; d < DEPTH - 1; ++d) pre.issue(d);
 
@@ -306,41 +314,42 @@ __global__ void __launch_bounds__(WPB * 32) march_grad(const GradArgs<T, KR, KS>
     for (int st = 0; st < NOUT; ++st)
 #pragma unroll
         for (int i = 0; i < P; ++i) acc[st][i] = T(0);
-    // plain-store byte offsets of the wide (lag 2R) and narrow (lag R+RS) streams
-    int64_t ooffR = (base + (int64_t)c0 * g.stride_march) * (int64_t)sizeof(T);
-    int64_t ooffS = ooffR;
+    // plain-store byte offsets of the output completed at step s by the wide (c0 + s - 2R) and narrow
+    // (c0 + s - R - RS) filters
+    int64_t ooffR = base * (int64_t)sizeof(T) + ((int64_t)c0 - 2 * R) * pre.stride_bytes;
+    int64_t ooffS = base * (int64_t)sizeof(T) + ((int64_t)c0 - R - RS) * pre.stride_bytes;
 
+    cp_async_wait<DEPTH - 2>();
+    T vn[NIN];
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) vn[i] = pre.read(0, i);
 #pragma unroll 1
     for (int s0 = 0; s0 < nsteps; s0 += P) {
 #pragma unroll
         for (int ph = 0; ph < P; ++ph) {
-            const int s = s0 + ph;
-            if (s < nsteps) {
-                pre.issue((ph + DEPTH - 1) % DEPTH);
-                cp_async_wait<DEPTH - 1>();
-                T v[NIN];
+            T v[NIN];
 #pragma unroll
-                for (int i = 0; i < NIN; ++i) v[i] = pre.read(ph % DEPTH, i);
-                const int jR = s - 2 * R;          // output index (relative to c0) the wide filters complete now
-                const int jS = s - R - RS;         // ... and the narrow filter
+            for (int i = 0; i < NIN; ++i) v[i] = vn[i];
+            pre.issue((ph + DEPTH - 1) % DEPTH);
+            cp_async_wait<DEPTH - 2>();            // step s+1 has landed: read it while step s is accumulated
 #pragma unroll
-                for (int st = 0; st < NOUT; ++st) {
-                    const int kd = kind[MODE][st];
-                    const T x = v[src[MODE][st]];
-                    T res; int j;
-                    if (kd == 2) { res = ring_push<T, KS, P>(acc[st], a.fS, x, ph); j = jS; }
-                    else { res = ring_push<T, KR, P>(acc[st], kd == 0 ? a.fG : a.fD, x, ph); j = jR; }
-                    if (TR) {
-                        tiles[(st * P + ph) * 33 + lane] = res;
-                    } else if (j >= 0 && j < nout && lane_ok) {
-                        *reinterpret_cast<T*>(reinterpret_cast<char*>(a.out[st]) + (kd == 2 ? ooffS : ooffR)) = res;
-                    }
-                }
-                if (!TR) {
-                    if (jR >= 0) ooffR += pre.stride_bytes;
-                    if (jS >= 0) ooffS += pre.stride_bytes;
+            for (int i = 0; i < NIN; ++i) vn[i] = pre.read((ph + 1) % DEPTH, i);
+            const bool okR = (unsigned)(s0 + ph - 2 * R) < nvalid;
+            const bool okS = (unsigned)(s0 + ph - R - RS) < nvalid;
+#pragma unroll
+            for (int st = 0; st < NOUT; ++st) {
+                const int kd = kind[MODE][st];
+                const T x = v[src[MODE][st]];
+                T res;
+                if (kd == 2) res = ring_push<T, KS, P>(acc[st], a.fS, x, ph);
+                else res = ring_push<T, KR, P>(acc[st], kd == 0 ? a.fG : a.fD, x, ph);
+                if (TR) {
+                    tiles[(st * P + ph) * 33 + lane] = res;
+                } else if (kd == 2 ? okS : okR) {
+                    *reinterpret_cast<T*>(reinterpret_cast<char*>(a.out[st]) + (kd == 2 ? ooffS : ooffR)) = res;
                 }
             }
+            if (!TR) { ooffR += pre.stride_bytes; ooffS += pre.stride_bytes; }
         }
         if (TR) {
 #pragma unroll 1
@@ -353,10 +362,14 @@ __global__ void __launch_bounds__(WPB * 32) march_grad(const GradArgs<T, KR, KS>
 }
 
 // ------------------------------------------------------------------------------------------------
-// Last window pass (march y, N layout, lanes on x) fused with the per-voxel solve and reliability:
-// the NCH warps of a block march the NCH channels of the same (z, x-group, y-chunk) in lock step,
-// park NCH completed rows in shared memory, and every NCH steps each warp solves one row
-// (calc_flow.py:337-357 / 154-168).  The window sums never go back to HBM.
+// Last window pass (march y, N layout, lanes on x) fused with the per-voxel solve and reliability
+// (calc_flow.py:337-357 / 154-168): the window sums never go back to HBM.
+//
+// The NCH warps of a block march the NCH channels of the same (z, x-group, y-chunk) and park every
+// completed row in shared memory.  After a batch of BR = NR*NCH rows the block synchronises once and each warp
+// solves NR rows of the batch, evaluated together so that the long dependent chains of the solve (reciprocal,
+// rsqrt, Newton steps of the eigenvalue) overlap (instruction-level parallelism).  The park is double-buffered,
+// so one barrier per batch is enough.
 template <typename T, int K>
 struct SolveArgs {
     MarchGeom g;
@@ -365,12 +378,17 @@ struct SolveArgs {
     T* vx; T* vy; T* vz; T* rel;
 };
 
+constexpr int kSolveRowsPerWarp = 3;
 template <typename T, int DEPTH, int NCH>
-constexpr size_t solve_smem() { return (size_t)(2 * NCH * NCH * 32 + NCH * Prefetcher<T, 1, DEPTH>::elems_per_warp) * sizeof(T); }
+constexpr size_t solve_smem() {
+    return (size_t)(2 * kSolveRowsPerWarp * NCH * NCH * 32 + NCH * Prefetcher<T, 1, DEPTH>::elems_per_warp) * sizeof(T);
+}
 
 template <typename T, int K, int P, int DEPTH, int NCH>
-__global__ void __launch_bounds__(NCH * 32) march_solve(const SolveArgs<T, K> a) {
-    static_assert(P >= K && P % NCH == 0 && P % DEPTH == 0, "bad unroll period");
+__global__ void __launch_bounds__(NCH * 32, 1) march_solve(const SolveArgs<T, K> a) {
+    constexpr int NR = kSolveRowsPerWarp;
+    constexpr int BR = NR * NCH;                            // rows per batch
+    static_assert(P >= K && P % BR == 0 && P % DEPTH == 0, "bad unroll period");
     constexpr int R = K / 2;
     using Pre = Prefetcher<T, 1, DEPTH>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -387,59 +405,86 @@ __global__ void __launch_bounds__(NCH * 32) march_solve(const SolveArgs<T, K> a)
     const int c0 = chunk * g.chunk;
     const int c1 = min(c0 + g.chunk, (int)g.n_march);
     const int64_t base = other * g.stride_other + lpos;
+    const int nout = c1 - c0;
+    const int nbatch = (nout + BR - 1) / BR;
 
     Pre pre;
-    pre.lbase = park + 2 * NCH * NCH * 32 + ch * Pre::elems_per_warp + lane;
+    pre.lbase = park + 2 * BR * NCH * 32 + ch * Pre::elems_per_warp + lane;
     pre.sbase = (uint32_t)__cvta_generic_to_shared(pre.lbase);
     pre.qpos = c0 - R;
     pre.n_march_m1 = (int)g.n_march - 1;
     pre.stride_bytes = g.stride_march * (int64_t)sizeof(T);
     pre.gp[0] = reinterpret_cast<const char*>(a.in + (int64_t)ch * g.vol + base + clampi(c0 - R, g.n_march) * g.stride_march);
 
-    // Outputs complete at steps s >= 2R.  The march is padded so that the number of output steps is a
-    // multiple of NCH (the last batch may hold fewer valid rows; padded inputs are clamped reads).
-    const int nout = c1 - c0;
-    const int nsteps = 2 * R + (nout + NCH - 1) / NCH * NCH;
+    // Outputs complete at steps s >= 2R; output j = s - 2R goes to row j mod BR of batch floor(j / BR).  The
+    // march is padded to whole unroll periods and has no branch per step: the steps before the first output fill
+    // "batch -1", which is solved like any other and masked at the store, as are the rows past the chunk end.
+    const int nsteps = (2 * R + nbatch * BR + P - 1) / P * P;
 #pragma unroll
     for (int d = 0; d < DEPTH - 1; ++d) pre.issue(d);
 
     T acc[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) acc[i] = T(0);
+    constexpr int kRowBias = (2 * R + BR - 1) / BR * BR;    // multiple of BR, >= 2R
+    int n = -(kRowBias / BR);                               // batch being filled (negative: warm-up); buffer n & 1
+    T* pk = park + ((n & 1) * BR * NCH * 32) + ch * 32 + lane;   // this warp's slot in row 0 of that buffer
 
+    cp_async_wait<DEPTH - 2>();
+    T vn = pre.read(0, 0);
 #pragma unroll 1
     for (int s0 = 0; s0 < nsteps; s0 += P) {
 #pragma unroll
         for (int ph = 0; ph < P; ++ph) {
-            const int s = s0 + ph;
-            if (s < nsteps) {      // block-uniform
-                pre.issue((ph + DEPTH - 1) % DEPTH);
-                cp_async_wait<DEPTH - 1>();
-                const T v = pre.read(ph % DEPTH, 0);
-                const T res = ring_push<T, K, P>(acc, a.f, v, ph);
-                const int j = s - 2 * R;
-                if (j >= 0) {
-                    const int row = (ph + NCH * P - 2 * R) % NCH;   // == j % NCH since NCH | P | s0
-                    const int buf = (j / NCH) & 1;
-                    park[((buf * NCH + row) * NCH + ch) * 32 + lane] = res;
-                    if (row == NCH - 1) {
-                        __syncthreads();
-                        // warp `ch` solves row `ch` of this batch
-                        const int jo = j - (NCH - 1) + ch;
-                        if (jo < nout && lane_ok) {
+            const T v = vn;
+            pre.issue((ph + DEPTH - 1) % DEPTH);
+            cp_async_wait<DEPTH - 2>();            // step s+1 has landed: read it while step s is accumulated
+            vn = pre.read((ph + 1) % DEPTH, 0);
+            const T res = ring_push<T, K, P>(acc, a.f, v, ph);
+            const int row = (ph + kRowBias - 2 * R) % BR;             // == (s - 2R) mod BR since BR | P | s0
+            pk[row * NCH * 32] = res;
+            if (row == BR - 1) {
+                __syncthreads();
+                // warp `ch` solves rows ch, ch + NCH, ... of this batch, together
+                const T* qb = park + ((n & 1) * BR + ch) * NCH * 32 + lane;
+                if (NCH == 9) {
+                    Flow3 r[NR];
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const T* qv = qb + i * NCH * NCH * 32;
+#ifdef OF3D_EXP_NOSOLVE
+                        r[i].vx = qv[0] + qv[32] + qv[64]; r[i].vy = qv[96] + qv[128]; r[i].vz = qv[160] + qv[192]; r[i].rel = qv[224] + qv[256];
+#else
+                        r[i] = solve3<false>((double)qv[0], (double)qv[32], (double)qv[64], (double)qv[96], (double)qv[128],
+                                             (double)qv[160], (double)qv[192], (double)qv[224], (double)qv[256]);
+#endif
+                    }
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const int jo = n * BR + ch + i * NCH;
+                        if (jo >= 0 && jo < nout && lane_ok) {
                             const int64_t idx = base + (int64_t)(c0 + jo) * g.stride_march;
-                            const T* qv = park + ((buf * NCH + ch) * NCH) * 32 + lane;
-                            if (NCH == 9) {
-                                const Flow3 r = solve3<false>((double)qv[0], (double)qv[32], (double)qv[64], (double)qv[96], (double)qv[128],
-                                                              (double)qv[160], (double)qv[192], (double)qv[224], (double)qv[256]);
-                                a.vx[idx] = (T)r.vx; a.vy[idx] = (T)r.vy; a.vz[idx] = (T)r.vz; a.rel[idx] = (T)r.rel;
-                            } else {
-                                const Flow2 r = solve2<false>((double)qv[0], (double)qv[32], (double)qv[64], (double)qv[96], (double)qv[128]);
-                                a.vx[idx] = (T)r.vx; a.vy[idx] = (T)r.vy; a.rel[idx] = (T)r.rel;
-                            }
+                            a.vx[idx] = (T)r[i].vx; a.vy[idx] = (T)r[i].vy; a.vz[idx] = (T)r[i].vz; a.rel[idx] = (T)r[i].rel;
+                        }
+                    }
+                } else {
+                    Flow2 r[NR];
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const T* qv = qb + i * NCH * NCH * 32;
+                        r[i] = solve2<false>((double)qv[0], (double)qv[32], (double)qv[64], (double)qv[96], (double)qv[128]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const int jo = n * BR + ch + i * NCH;
+                        if (jo >= 0 && jo < nout && lane_ok) {
+                            const int64_t idx = base + (int64_t)(c0 + jo) * g.stride_march;
+                            a.vx[idx] = (T)r[i].vx; a.vy[idx] = (T)r[i].vy; a.rel[idx] = (T)r[i].rel;
                         }
                     }
                 }
+                ++n;
+                pk = park + ((n & 1) * BR * NCH * 32) + ch * 32 + lane;
             }
         }
     }

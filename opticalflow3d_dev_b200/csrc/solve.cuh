@@ -13,6 +13,25 @@ constexpr double kEps = 2.220446049250313e-16;  // np.finfo(float).eps, calc_flo
 struct Flow3 { double vx, vy, vz, rel; };
 struct Flow2 { double vx, vy, rel; };
 
+// Branch-free double-precision reciprocal and reciprocal square root: hardware seed (MUFU.RCP64H / RSQ64H,
+// 20 mantissa bits, full exponent range) plus two Newton steps -> ~1 ulp.  No slow-path branch, so several
+// voxels' dependency chains can be interleaved by the compiler (the IEEE division's fix-up branch prevents that).
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    return y;
+}
+
 // Smallest eigenvalue of the symmetric matrix [[xx,xy,xz],[xy,yy,yz],[xz,yz,zz]].
 // The reference runs LAPACK cgeev on complex64 (float32 accuracy); for a real symmetric matrix the
 // eigenvalues are real and the lexicographic complex minimum is the smallest one, which is what this
@@ -24,43 +43,40 @@ struct Flow2 { double vx, vy, rel; };
 // so the root is found instead on the shifted cubic: with s = t + 1/2 in [-1/2, 0] and e = 1 - r in [0, 2],
 //     s^2 (4s - 6) + e = 0 .
 // The seed is the fp32 fixed-point iterate of s = -sqrt(e / (6 - 4s)) (contraction rate < 0.19, exact as
-// e -> 0), polished by Newton steps in fp64 whose slope reciprocal only needs fp32 accuracy because Newton
-// is self-correcting.  In this form the convergence is quadratic in the RELATIVE error of s, also next to the
-// double root (two equal smallest eigenvalues, e -> 0) where the trigonometric form loses half the digits.
+// e -> 0; relative error < 6e-3 after two rounds), polished by three Newton steps in fp64 whose slope
+// reciprocal only needs fp32 accuracy because Newton is self-correcting.  In this form the convergence is
+// quadratic in the RELATIVE error of s, also next to the double root (two equal smallest eigenvalues, e -> 0)
+// where the trigonometric form loses half the digits.  The whole function is straight-line code (selects
+// instead of branches).
 __device__ __forceinline__ double min_eig_sym3(double xx, double xy, double xz, double yy, double yz, double zz) {
     const double q = (xx + yy + zz) * (1.0 / 3.0);
     const double a = xx - q, b = yy - q, c = zz - q;
     const double p1 = xy * xy + xz * xz + yz * yz;
     const double p2 = (a * a + b * b + c * c + 2.0 * p1) * (1.0 / 6.0);
-    if (!(p2 > 0.0)) return q;  // scalar matrix (incl. all-zero): every eigenvalue is q
-    // ip = 1/sqrt(p2): fp32 seed + two fp64 Newton steps; library path when p2 leaves the float range
-    double ip = (double)rsqrtf((float)p2);
-    if (!(ip > 0.0) || ip > 1e30) ip = rsqrt(p2);
-    else {
-        ip = ip * (1.5 - 0.5 * p2 * ip * ip);
-        ip = ip * (1.5 - 0.5 * p2 * ip * ip);
-    }
+    const bool scalar = !(p2 > 0.0);                 // scalar matrix (incl. all-zero): every eigenvalue is q
+    const double ip = rsqrt_fast(scalar ? 1.0 : p2);
     const double p = p2 * ip;
     const double ba = a * ip, bb = b * ip, bc = c * ip, bxy = xy * ip, bxz = xz * ip, byz = yz * ip;
     double r = 0.5 * (ba * (bb * bc - byz * byz) - bxy * (bxy * bc - byz * bxz) + bxz * (bxy * byz - bb * bxz));
     r = fmin(1.0, fmax(-1.0, r));
     const double e = 1.0 - r;
-    const float ef = (float)e;
-    double s = 0.0;
-    if (ef > 0.0f) {
-        float sf = -sqrtf(ef * (1.0f / 6.0f));
+    const float ef = fmaxf((float)e, 1e-30f);
+    float sf = -ef * rsqrtf(ef * 6.0f);              // -sqrt(e/6)
 #pragma unroll
-        for (int it = 0; it < 4; ++it) sf = -sqrtf(__fdividef(ef, 6.0f - 4.0f * sf));
-        s = (double)sf;
-#pragma unroll
-        for (int it = 0; it < 3; ++it) {
-            const double f = s * s * (4.0 * s - 6.0) + e;
-            const double fp = 12.0 * s * (s - 1.0);            // > 0 for s < 0
-            s -= f * (double)__frcp_rn((float)fp);
-        }
-        s = fmin(0.0, fmax(-0.5, s));
+    for (int it = 0; it < 2; ++it) {
+        const float d = 6.0f - 4.0f * sf;            // in [6, 8]
+        sf = -ef * rsqrtf(ef * d);                   // -sqrt(e/d)
     }
-    return (q - p) + 2.0 * p * s;
+    double s = (double)sf;
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const double f = s * s * (4.0 * s - 6.0) + e;
+        const double fp = 12.0 * s * (s - 1.0);      // > 0 for s < 0
+        s -= f * (double)__frcp_rn((float)fp);
+    }
+    s = fmin(0.0, fmax(-0.5, s));
+    const double lam = (q - p) + 2.0 * p * s;
+    return scalar ? q : lam;
 }
 
 // EXACT = true reproduces NumPy's evaluation order with individually rounded operations
@@ -91,7 +107,7 @@ __device__ __forceinline__ Flow3 solve3(double xx, double xy, double xz, double 
         // Sarrus determinant written exactly as the reference does (cofactor expansion would
         // round differently where the tensor is near-singular)
         const double det = xx * yy * zz + 2.0 * xy * xz * yz - yy * xz * xz - zz * xy * xy - xx * yz * yz;
-        const double ninv = -1.0 / (det + kEps);
+        const double ninv = -rcp_fast(det + kEps);
         o.vx = ninv * (cxx * tx + cxy * ty + cxz * tz);
         o.vy = ninv * (cxy * tx + cyy * ty + cyz * tz);
         o.vz = ninv * (cxz * tx + cyz * ty + czz * tz);

@@ -54,5 +54,10 @@ int main() {
     }
     run<double, 16>("fp64", sms, 4, 20000);
     run<float, 16>("fp32", sms, 4, 40000);
+    // low occupancy: 256 threads per SM = 2 warps per scheduler (the marching kernels' regime)
+    run<double, 8>("fp64_2warps_per_sched", sms, 1, 20000);
+    run<double, 24>("fp64_2warps_per_sched", sms, 1, 20000);
+    run<float, 8>("fp32_2warps_per_sched", sms, 1, 40000);
+    run<float, 24>("fp32_2warps_per_sched", sms, 1, 40000);
     return 0;
 }
