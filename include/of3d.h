@@ -131,6 +131,22 @@ OF3D_API int of3d_flow_frames(of3d_ctx* ctx, int ndim, const void* const* frames
                      const of3d_taps* taps, int precision, unsigned flags,
                      void* vx, void* vy, void* vz, void* rel, int out_mem);
 
+/*
+ * The operator in two stages, for volumes sharded by z-slab across GPUs.  The temporal
+ * derivative (calc_flow.py:276-278) is local in z, the spatial stages are not: a rank runs stage 1 on the planes
+ * it owns, exchanges R + Rw halo planes of (ic, dt0) with its neighbours (NCCL), runs stage 2 on the extended slab
+ * and keeps the planes it owns.
+ *   of3d_temporal     frames -> ic (centre frame widened to the compute type) and dt0 (temporal derivative),
+ *                     both DEVICE buffers (nz, ny, nx) of double (OF3D_FP64) or float (OF3D_FP32).
+ *   of3d_flow_from_dt (ic, dt0) device buffers -> vx, vy, vz, rel (calc_flow.py:279-357 / 116-168).
+ */
+OF3D_API int of3d_temporal(of3d_ctx* ctx, int ndim, const void* const* frames, int in_dtype, int in_mem,
+                           int64_t nz, int64_t ny, int64_t nx, const of3d_taps* taps, int precision, unsigned flags,
+                           void* ic_dev, void* dt0_dev);
+OF3D_API int of3d_flow_from_dt(of3d_ctx* ctx, int ndim, const void* ic_dev, const void* dt0_dev,
+                               int64_t nz, int64_t ny, int64_t nx, const of3d_taps* taps, int precision, unsigned flags,
+                               void* vx, void* vy, void* vz, void* rel, int out_mem);
+
 /* Stream control: the context's stream as a cudaStream_t (for CUDA-event timing by the caller),
  * asynchronous mode (device in/out only: calls return after enqueueing), and a sync. */
 OF3D_API void* of3d_stream(of3d_ctx* ctx);

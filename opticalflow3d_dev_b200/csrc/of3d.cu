@@ -131,10 +131,9 @@ struct GenericPipe {
         return OF3D_OK;
     }
 
-    int run(const FramePtrs& fp, int in_dtype, T* vx, T* vy, T* vz, T* rel) {
+    // everything after the temporal stage: ic = widened centre frame, dt0 = temporal derivative
+    int run_spatial(const T* ic, const T* dt0, T* vx, T* vy, T* vz, T* rel) {
         const int64_t n = s.n();
-        T* ic = ws_take<T>(c, n);
-        T* dt0 = ws_take<T>(c, n);
         T* t1 = ws_take<T>(c, n);
         T* t2 = ws_take<T>(c, n);
         T* dt = ws_take<T>(c, n);
@@ -144,7 +143,6 @@ struct GenericPipe {
         T* prod = ws_take<T>(c, n);
         const int nch = s.ndim == 3 ? 9 : 5;
         T* w = ws_take<T>(c, (size_t)nch * n);
-        if (int rc = run_temporal(fp, in_dtype, ic, dt0)) return rc;
         chain(dt0, dt, t1, t2, fG, fG, fG);          // calc_flow.py:279 / 116
         chain(ic, dy, t1, t2, fD, fS, fS);           // :282 / 119
         chain(ic, dx, t1, t2, fS, fD, fS);           // :285 / 122
@@ -185,80 +183,109 @@ static int check_taps(const of3d_taps* t) {
     return OF3D_OK;
 }
 
-template <typename T>
-static int run_typed(of3d_ctx* c, const Shape& s, const FramePtrs& fp, int in_dtype, const of3d_taps* t, unsigned flags,
-                     T* vx, T* vy, T* vz, T* rel) {
-    if (flags & OF3D_FLAG_EXACT) {
-        GenericPipe<T, true> g{c, s, make_filt<T>(t->D, t->nD), make_filt<T>(t->S, t->nS), make_filt<T>(t->G, t->nG),
-                               make_filt<T>(t->T, t->nT), make_filt<T>(t->W, t->nW)};
-        return g.run(fp, in_dtype, vx, vy, vz, rel);
-    }
-    GenericPipe<T, false> g{c, s, make_filt<T>(t->D, t->nD), make_filt<T>(t->S, t->nS), make_filt<T>(t->G, t->nG),
+// fp != nullptr: run the temporal stage on the frames into (ic_out, dt0_out) (workspace if null);
+// fp == nullptr: (ic_in, dt0_in) are given.  spatial == false stops after the temporal stage.
+template <typename T, bool EXACT>
+static int run_pipe(of3d_ctx* c, const Shape& s, const FramePtrs* fp, int in_dtype, const of3d_taps* t, unsigned flags,
+                    const T* ic_in, const T* dt0_in, T* ic_out, T* dt0_out, bool spatial, T* vx, T* vy, T* vz, T* rel) {
+    GenericPipe<T, EXACT> g{c, s, make_filt<T>(t->D, t->nD), make_filt<T>(t->S, t->nS), make_filt<T>(t->G, t->nG),
                             make_filt<T>(t->T, t->nT), make_filt<T>(t->W, t->nW)};
-    if (!(flags & OF3D_FLAG_GENERIC) && fast_supported(t)) {
-        // marching-kernel pipeline: temporal derivative (elementwise), then kernels_march.cuh
-        T* ic = ws_take<T>(c, s.n());
-        T* dt0 = ws_take<T>(c, s.n());
-        if (int rc = g.run_temporal(fp, in_dtype, ic, dt0)) return rc;
-        const int rc = run_fast<T>(c, s, ic, dt0, t, vx, vy, vz, rel);
-        if (rc != kNotSupported) return rc;
-        c->ws_off -= 2 * align_up((size_t)s.n() * sizeof(T));
+    const T* ic = ic_in; const T* dt0 = dt0_in;
+    if (fp) {
+        T* a = ic_out ? ic_out : ws_take<T>(c, s.n());
+        T* b = dt0_out ? dt0_out : ws_take<T>(c, s.n());
+        if (int rc = g.run_temporal(*fp, in_dtype, a, b)) return rc;
+        ic = a; dt0 = b;
     }
-    return g.run(fp, in_dtype, vx, vy, vz, rel);
+    if (!spatial) return OF3D_OK;
+    if (!EXACT && !(flags & OF3D_FLAG_GENERIC) && fast_supported(t)) {
+        const int rc = run_fast<T>(c, s, ic, dt0, t, vx, vy, vz, rel);   // marching kernels (kernels_march.cuh)
+        if (rc != kNotSupported) return rc;
+    }
+    return g.run_spatial(ic, dt0, vx, vy, vz, rel);
 }
 
-static int flow_frames_impl(of3d_ctx* c, int ndim, const void* const* frames, int in_dtype, int in_mem, int64_t nz,
-                            int64_t ny, int64_t nx, const of3d_taps* t, int precision, unsigned flags, void* vx, void* vy,
-                            void* vz, void* rel, int out_mem) {
+template <typename T>
+static int run_typed(of3d_ctx* c, const Shape& s, const FramePtrs* fp, int in_dtype, const of3d_taps* t, unsigned flags,
+                     const void* ic_in, const void* dt0_in, void* ic_out, void* dt0_out, bool spatial, void* const dout[4]) {
+    if (flags & OF3D_FLAG_EXACT)
+        return run_pipe<T, true>(c, s, fp, in_dtype, t, flags, (const T*)ic_in, (const T*)dt0_in, (T*)ic_out, (T*)dt0_out, spatial,
+                                 (T*)dout[0], (T*)dout[1], (T*)dout[2], (T*)dout[3]);
+    return run_pipe<T, false>(c, s, fp, in_dtype, t, flags, (const T*)ic_in, (const T*)dt0_in, (T*)ic_out, (T*)dt0_out, spatial,
+                              (T*)dout[0], (T*)dout[1], (T*)dout[2], (T*)dout[3]);
+}
+
+// stage: 0 = whole operator from frames, 1 = temporal stage only (frames -> ic, dt0 device buffers),
+//        2 = spatial stages from (ic, dt0) device buffers
+static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* frames, int in_dtype, int in_mem, int64_t nz,
+                       int64_t ny, int64_t nx, const of3d_taps* t, int precision, unsigned flags, void* ic_dev, void* dt0_dev,
+                       void* vx, void* vy, void* vz, void* rel, int out_mem) {
     if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
     if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3"); return OF3D_ERR_ARG; }
     if (int rc = check_taps(t)) return rc;
     if (nz < 1 || ny < 1 || nx < 1 || (ndim == 2 && nz != 1)) { set_error("bad volume shape"); return OF3D_ERR_ARG; }
-    if (!dtype_size(in_dtype)) { set_error("unsupported input dtype"); return OF3D_ERR_ARG; }
     if (precision != OF3D_FP64 && precision != OF3D_FP32) { set_error("precision must be OF3D_FP64 or OF3D_FP32"); return OF3D_ERR_ARG; }
     if ((in_mem != OF3D_HOST && in_mem != OF3D_DEVICE) || (out_mem != OF3D_HOST && out_mem != OF3D_DEVICE)) { set_error("bad memory space"); return OF3D_ERR_ARG; }
-    if (!frames || !vx || !vy || !rel || (ndim == 3 && !vz)) { set_error("null image or output pointer"); return OF3D_ERR_ARG; }
-    for (int k = 0; k < t->nT; ++k) if (!frames[k]) { set_error("null frame pointer"); return OF3D_ERR_ARG; }
+    if (stage != 2) {
+        if (!dtype_size(in_dtype)) { set_error("unsupported input dtype"); return OF3D_ERR_ARG; }
+        if (!frames) { set_error("null image pointer"); return OF3D_ERR_ARG; }
+        for (int k = 0; k < t->nT; ++k) if (!frames[k]) { set_error("null frame pointer"); return OF3D_ERR_ARG; }
+    }
+    if (stage != 0 && (!ic_dev || !dt0_dev)) { set_error("null ic/dt0 pointer"); return OF3D_ERR_ARG; }
+    if (stage != 1 && (!vx || !vy || !rel || (ndim == 3 && !vz))) { set_error("null image or output pointer"); return OF3D_ERR_ARG; }
     OF3D_CUDA_TRY(cudaSetDevice(c->device));
 
     const Shape s{ndim, nz, ny, nx};
     const int64_t n = s.n();
     const size_t ts = precision == OF3D_FP32 ? 4 : 8;
-    if (int rc = ws_ensure(c, plan_bytes(ndim, t->nT, n, in_dtype, precision, in_mem, out_mem))) return rc;
+    if (int rc = ws_ensure(c, plan_bytes(ndim, stage == 2 ? 0 : t->nT, n, in_dtype, precision, stage == 2 ? OF3D_DEVICE : in_mem,
+                                         stage == 1 ? OF3D_DEVICE : out_mem))) return rc;
     c->ws_off = 0;
 
     FramePtrs fp;
     memset(&fp, 0, sizeof(fp));
-    if (in_mem == OF3D_HOST) {
-        const size_t fb = (size_t)n * dtype_size(in_dtype);
-        for (int k = 0; k < t->nT; ++k) {
-            char* d = ws_take<char>(c, fb);
-            OF3D_CUDA_TRY(cudaMemcpyAsync(d, frames[k], fb, cudaMemcpyHostToDevice, c->stream));
-            fp.p[k] = d;
+    if (stage != 2) {
+        if (in_mem == OF3D_HOST) {
+            const size_t fb = (size_t)n * dtype_size(in_dtype);
+            for (int k = 0; k < t->nT; ++k) {
+                char* d = ws_take<char>(c, fb);
+                OF3D_CUDA_TRY(cudaMemcpyAsync(d, frames[k], fb, cudaMemcpyHostToDevice, c->stream));
+                fp.p[k] = d;
+            }
+        } else {
+            for (int k = 0; k < t->nT; ++k) fp.p[k] = frames[k];
         }
-    } else {
-        for (int k = 0; k < t->nT; ++k) fp.p[k] = frames[k];
     }
     void* out[4] = {vx, vy, vz, rel};
     void* dout[4] = {vx, vy, vz, rel};
     const int nout = ndim + 1;
     const int oidx3[4] = {0, 1, 2, 3}, oidx2[3] = {0, 1, 3};
     const int* oidx = ndim == 3 ? oidx3 : oidx2;
-    if (out_mem == OF3D_HOST)
+    if (stage != 1 && out_mem == OF3D_HOST)
         for (int i = 0; i < nout; ++i) dout[oidx[i]] = ws_take<char>(c, (size_t)n * ts);
 
+    const FramePtrs* fpp = stage == 2 ? nullptr : &fp;
     int rc;
     if (precision == OF3D_FP64)
-        rc = run_typed<double>(c, s, fp, in_dtype, t, flags, (double*)dout[0], (double*)dout[1], (double*)dout[2], (double*)dout[3]);
+        rc = run_typed<double>(c, s, fpp, in_dtype, t, flags, ic_dev, dt0_dev, stage == 1 ? ic_dev : nullptr,
+                               stage == 1 ? dt0_dev : nullptr, stage != 1, dout);
     else
-        rc = run_typed<float>(c, s, fp, in_dtype, t, flags, (float*)dout[0], (float*)dout[1], (float*)dout[2], (float*)dout[3]);
+        rc = run_typed<float>(c, s, fpp, in_dtype, t, flags, ic_dev, dt0_dev, stage == 1 ? ic_dev : nullptr,
+                              stage == 1 ? dt0_dev : nullptr, stage != 1, dout);
     if (rc) return rc;
     OF3D_CUDA_TRY(cudaGetLastError());
-    if (out_mem == OF3D_HOST)
+    if (stage != 1 && out_mem == OF3D_HOST)
         for (int i = 0; i < nout; ++i)
             OF3D_CUDA_TRY(cudaMemcpyAsync(out[oidx[i]], dout[oidx[i]], (size_t)n * ts, cudaMemcpyDeviceToHost, c->stream));
-    if (!(c->async && in_mem == OF3D_DEVICE && out_mem == OF3D_DEVICE)) OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const bool all_device = (stage == 2 || in_mem == OF3D_DEVICE) && (stage == 1 || out_mem == OF3D_DEVICE);
+    if (!(c->async && all_device)) OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return OF3D_OK;
+}
+
+static int flow_frames_impl(of3d_ctx* c, int ndim, const void* const* frames, int in_dtype, int in_mem, int64_t nz,
+                            int64_t ny, int64_t nx, const of3d_taps* t, int precision, unsigned flags, void* vx, void* vy,
+                            void* vz, void* rel, int out_mem) {
+    return flow_staged(c, 0, ndim, frames, in_dtype, in_mem, nz, ny, nx, t, precision, flags, nullptr, nullptr, vx, vy, vz, rel, out_mem);
 }
 
 static int flow_contig(of3d_ctx* c, int ndim, const void* images, int in_dtype, int in_mem, int64_t nt, int64_t nz, int64_t ny,
@@ -347,6 +374,19 @@ OF3D_API int of3d_flow_frames(of3d_ctx* ctx, int ndim, const void* const* frames
                      int64_t nx, const of3d_taps* taps, int precision, unsigned flags, void* vx, void* vy, void* vz, void* rel,
                      int out_mem) {
     return flow_frames_impl(ctx, ndim, frames, in_dtype, in_mem, nz, ny, nx, taps, precision, flags, vx, vy, vz, rel, out_mem);
+}
+
+OF3D_API int of3d_temporal(of3d_ctx* ctx, int ndim, const void* const* frames, int in_dtype, int in_mem, int64_t nz, int64_t ny,
+                           int64_t nx, const of3d_taps* taps, int precision, unsigned flags, void* ic_dev, void* dt0_dev) {
+    return flow_staged(ctx, 1, ndim, frames, in_dtype, in_mem, nz, ny, nx, taps, precision, flags, ic_dev, dt0_dev, nullptr, nullptr,
+                       nullptr, nullptr, OF3D_DEVICE);
+}
+
+OF3D_API int of3d_flow_from_dt(of3d_ctx* ctx, int ndim, const void* ic_dev, const void* dt0_dev, int64_t nz, int64_t ny, int64_t nx,
+                               const of3d_taps* taps, int precision, unsigned flags, void* vx, void* vy, void* vz, void* rel,
+                               int out_mem) {
+    return flow_staged(ctx, 2, ndim, nullptr, OF3D_U16, OF3D_DEVICE, nz, ny, nx, taps, precision, flags, const_cast<void*>(ic_dev),
+                       const_cast<void*>(dt0_dev), vx, vy, vz, rel, out_mem);
 }
 
 OF3D_API void* of3d_stream(of3d_ctx* c) { return c ? (void*)c->stream : nullptr; }
