@@ -331,6 +331,13 @@ def gpu_arm(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def _finish(world):
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -358,6 +365,7 @@ def main():
                '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 1000)] + sys.argv
         os.execv(sys.executable, cmd)
     gpu_arm(args, rank, world, local_rank)
+    _finish(world)
 
 
 if __name__ == '__main__':
