@@ -118,11 +118,20 @@ __global__ void __launch_bounds__(NCH * kStripTX, 1) strip_window_solve(const St
     T* g_dst = xw + g_r * kXwRow + g_b * (XB + 1);
     const T* m_src = xw + lane + lane / 8;
     T* m_dst = park + ch * TX + 32 * half + lane;
-    const int s_i = TR ? (t % RB) : (t / TX);          // output row within the batch
-    const int s_col = TR ? (t / RB) : (t % TX);
-    const bool s_active = t < RB * TX;
-    const int s_c = cs0 + s_col;
-
+    // Solve work is handed out in units of 32 voxels (RB * TX / 32 = 16 units per batch).  A block has 18 warps on 4
+    // schedulers (warp % 4): two schedulers run 5 window warps, two run 4.  The lighter schedulers take more solve
+    // units (5 each) than the heavier ones (3 each), which evens out the FP64 work per scheduler.
+    constexpr int NUNITS = RB * TX / 32;
+    int su[2] = {-1, -1};
+    if (NCH == 9) {
+        const int q = warp >> 2, sm = warp & 3;                               // q-th warp of scheduler sm
+        if (sm >= 2) { su[0] = (sm - 2) * 5 + q; if (q == 0) su[1] = (sm - 2) * 5 + 4; }   // 4 warps, 5 units
+        else if (q < 3) su[0] = 10 + sm * 3 + q;                              // 5 warps, 3 units
+    } else {
+        su[0] = warp < NUNITS ? warp : -1;
+        su[1] = warp + 2 * NCH < NUNITS ? warp + 2 * NCH : -1;
+    }
+    static_assert(NCH != 9 || NUNITS == 16, "unit table assumes 16 units");
     T acc[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) acc[i] = T(0);
@@ -167,9 +176,15 @@ __global__ void __launch_bounds__(NCH * kStripTX, 1) strip_window_solve(const St
             }
             __syncthreads();                                                  // one batch of outputs parked by all channels
             // ---------------- solve: outputs j0 .. j0 + RB - 1 of batch b
-            {
+#pragma unroll
+            for (int ui = 0; ui < 2; ++ui) {
+                if (su[ui] < 0) continue;                                     // warp-uniform
+                const int v = su[ui] * 32 + lane;                             // voxel of the RB x TX batch
+                const int s_i = TR ? (v % RB) : (v / TX);                     // output row within the batch
+                const int s_col = TR ? (v / RB) : (v % TX);
+                const int s_c = cs0 + s_col;
                 const int j = b * RB - 2 * R + s_i;
-                if (s_active && j >= 0 && j < nout && s_c < a.n_c) {
+                if (j >= 0 && j < nout && s_c < a.n_c) {
                     const int prow = ((j % RB) + RB) % RB;
                     const T* qv = park + ((b & 1) * RB + prow) * PARKROW + s_col;
                     const int64_t idx = TR ? ((int64_t)o * a.stride_o + (int64_t)s_c * a.n_m + (m0 + j))
