@@ -93,6 +93,6 @@ static inline int window_class(const of3d_taps* t) {
 }
 static inline bool fast_supported(const of3d_taps* t) { return spatial_class(t) >= 0 && window_class(t) >= 0; }
 // workspace volumes of compute type used by run_fast (excluding ic and dt0)
-static inline int fast_volumes(int ndim) { return ndim == 3 ? 9 + 4 + 9 : 3 + 3 + 5; }
+static inline int fast_volumes(int ndim) { return ndim == 3 ? 9 + 4 : 3; }
 
 }  // namespace of3d

@@ -1,25 +1,19 @@
-// Plane-strip kernel: the last TWO window passes and the per-voxel solve in one launch.  Internal header.
+// Plane-strip kernels: the two in-plane passes of a separable stage in ONE launch.  Internal header.
 //
-// A block owns a strip of TX = 64 positions of the contiguous axis ("c") of one plane and marches along the
-// other in-plane axis ("m") in batches of RB = 8 rows.  It has NCH * 2 warps: warp (channel ch, half h) owns the
-// 32 columns [cs0 + 32 h, cs0 + 32 h + 32) of channel ch, and everything up to the solve is private to the warp
-// (only __syncwarp):
-//   load    cp.async of the warp's RB rows x (32 + K - 1) columns into its shared-memory rows (clamp-to-edge on
-//           the source address), issued one batch ahead;
-//   gather  window along c: lane (row r = l/4, block b = l%4) produces 8 consecutive outputs of row r from the row
-//           in shared memory -- 8 accumulators, 8 + K - 1 LDS, 8*K FMAs, all addresses and taps static.  Rows are
+// A warp owns 32 columns of the contiguous axis x ("c") of one plane and marches along y ("m") in batches of
+// RB = 8 rows; everything before a cross-channel step is private to the warp (only __syncwarp):
+//   load    cp.async of the warp's RB rows x (32 + Kg - 1) columns into its shared-memory rows (clamp-to-edge on the
+//           source address), issued one batch ahead;
+//   gather  filter along x: lane (row r = l/4, block b = l%4) produces 8 consecutive outputs of row r from the row in
+//           shared memory -- 8 accumulators, 8 + Kg - 1 LDS, 8*Kg FMAs, all addresses and taps static.  Rows are
 //           stored "blocked-transposed" (element e at (e % 8) * PITCH + e / 8) so that lanes read consecutive words;
-//   march   window along m: lane = column; the gathered value of each of the RB rows is scattered into the K
-//           register accumulators (same statically rotated ring as kernels_march.cuh); completed sums are parked in
-//           shared memory for the whole block.
-// Then ONE block barrier per batch, and every thread solves one voxel of the RB x TX batch (calc_flow.py:337-357)
-// and stores vx, vy, vz, rel.  The park is double-buffered, so warps may run up to a batch apart: the latency-bound
-// solve of one warp overlaps the FMA-bound gather/march of others.  The 9 window sums exist only in registers and
-// shared memory: compared with separate x and y passes this removes a 72 B/voxel write and a 72 B/voxel read of HBM
-// (fp64) and one launch.
+//   march   filter along y: lane = column; the gathered value of each of the RB rows is scattered into K register
+//           accumulators (the statically rotated ring of kernels_march.cuh).
 //
-// With TR the input is in T layout (z, x, y): c = y, m = x, and the outputs are written transposed, i.e. in
-// N layout (z, y, x) as the C ABI requires.
+// strip_grad          gradient stage: (dt0, ic) -> the four pre-z gradient volumes (calc_flow.py:279-288 x and y
+//                     passes) or, in 2D, dt, dy, dx (calc_flow.py:116-122).  Three independent warp roles.
+// strip_window_solve  window x pass + y pass + per-voxel solve (calc_flow.py:300-357 / 133-168): the NCH window
+//                     sums of a voxel only ever exist in registers and shared memory.
 #pragma once
 #include "common.cuh"
 #include "kernels_march.cuh"
@@ -27,116 +21,279 @@
 
 namespace of3d {
 
-constexpr int kStripTX = 64;   // strip width along the contiguous axis (two warps of 32 columns per channel)
 constexpr int kStripRB = 8;    // rows per batch
 constexpr int kStripXB = 8;    // outputs per lane in the gather phase
 
 template <int K> constexpr int strip_rowlen() { return 32 + K - 1; }
-template <int K> constexpr int strip_nblk() { return (strip_rowlen<K>() + 7) / 8; }
-template <int K> constexpr int strip_pitch() { return strip_nblk<K>() | 1; }
+template <int K> constexpr int strip_pitch() { return ((strip_rowlen<K>() + 7) / 8) | 1; }
 // row stride = 4 (mod 16) elements: the four rows a half-warp reads in the gather fall on disjoint banks
 template <int K> constexpr int strip_rowstride() { return (8 * strip_pitch<K>() + 11) / 16 * 16 + 4; }
 constexpr int kXwRow = 32 + 4;                                               // one pad element every 8 columns
-template <int NCH> constexpr int strip_parkrow() { return NCH * kStripTX + 2; }
-template <int K> constexpr int strip_warp_elems() { return kStripRB * strip_rowstride<K>() + kStripRB * kXwRow; }
 
-template <typename T, int K, int NCH>
-constexpr size_t strip_smem() {
-    return (size_t)(2 * NCH * strip_warp_elems<K>() + 2 * kStripRB * strip_parkrow<NCH>()) * sizeof(T);
-}
-
-template <typename T, int K>
-struct StripArgs {
-    Taps<T, K> f;
-    const T* in;            // channel-major volumes
-    T* vx; T* vy; T* vz; T* rel;
-    int64_t vol;            // elements per channel
-    int64_t stride_m;       // element stride of the march axis (input)
-    int64_t stride_o;       // element stride of the remaining axis (input and output)
-    int n_c, n_m, n_o;      // extents: contiguous, march, other
-    int chunk, n_chunks;    // outputs per block along m
+// Geometry shared by both kernels: N layout (other = z, march = y, contiguous = x)
+struct StripGeom {
+    int64_t vol;            // elements per volume
+    int64_t stride_m;       // element stride of y
+    int64_t stride_o;       // element stride of z
+    int n_c, n_m, n_o;      // extents x, y, z
+    int chunk, n_chunks;    // outputs per task along y
 };
 
-template <typename T, int K, int P, int NCH, bool TR>
-__global__ void __launch_bounds__(NCH * kStripTX, 1) strip_window_solve(const StripArgs<T, K> a) {
-    constexpr int TX = kStripTX, RB = kStripRB, XB = kStripXB, R = K / 2;
-    constexpr int ROWLEN = strip_rowlen<K>(), PITCH = strip_pitch<K>(), ROWSTRIDE = strip_rowstride<K>();
-    constexpr int PARKROW = strip_parkrow<NCH>();
-    constexpr int NLOAD = (ROWLEN + 7) / 8;                                  // cp.async per lane per row pass
-    static_assert(P >= K && P % RB == 0, "unroll period must cover the taps and be a multiple of the batch");
-    static_assert(ROWSTRIDE >= 8 * PITCH, "row stride too small");
+// Warp-private staging: one or two row buffers (blocked-transposed) and the gathered rows
+template <typename T, int KG, int NIN>
+struct StripStage {
+    static constexpr int ROWLEN = strip_rowlen<KG>(), PITCH = strip_pitch<KG>(), ROWSTRIDE = strip_rowstride<KG>();
+    static constexpr int NLOAD = (ROWLEN + 7) / 8;
+    static constexpr int elems = NIN * kStripRB * ROWSTRIDE + kStripRB * kXwRow;
+    T* rows;                // [NIN][RB][ROWSTRIDE]
+    T* xw;                  // [RB][kXwRow]
+    uint32_t rows_s;
+    const T* src[NIN];      // plane base of each input (already offset to z and channel)
+    int c0;                 // first column this lane loads (cw0 - R + lane % 8)
+    int ncm1, nmm1, mfirst; // clamp limits; row index of batch 0, row 0
+    int64_t stride_m;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* smem = reinterpret_cast<T*>(smem_raw);
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int ch = warp % NCH, half = warp / NCH;
-    T* rows = smem + warp * strip_warp_elems<K>();                           // [RB][ROWSTRIDE], private to the warp
-    T* xw = rows + RB * ROWSTRIDE;                                           // [RB][kXwRow], private to the warp
-    T* park = smem + 2 * NCH * strip_warp_elems<K>();                        // [2][RB][PARKROW], shared by the block
-    const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
-
-    int task = blockIdx.x;
-    const int nstrips = (a.n_c + TX - 1) / TX;
-    const int strip = task % nstrips; task /= nstrips;
-    const int chunk = task % a.n_chunks;
-    const int o = task / a.n_chunks;
-    const int cs0 = strip * TX;                                              // first column of the block's strip
-    const int cw0 = cs0 + 32 * half;                                         // first column of this warp
-    const int m0 = chunk * a.chunk;
-    const int m1 = min(m0 + a.chunk, a.n_m);
-    const int nout = m1 - m0;
-    const int nsteps = (nout + 2 * R + P - 1) / P * P;                       // whole unroll periods
-    const T* in_c = a.in + (int64_t)o * a.stride_o + (int64_t)ch * a.vol;
-
-    // ---- loader: lane (l8 = lane % 8, rr = lane / 8) fetches elements e = l8 + 8 i of rows rr and rr + 4; element e
-    // lives at (e % 8) * PITCH + e / 8 = l8 * PITCH + i.  Clamp-to-edge along c on the source column, along m on the row.
-    const int l8 = lane & 7, lrr = lane >> 3;
-    const int l_c0 = cw0 - R + l8;
-    const int ncm1 = a.n_c - 1, nmm1 = a.n_m - 1;
-    auto issue_batch = [&](int b) {
+    __device__ __forceinline__ void init(T* smem_warp, int cw0, int m_first, const StripGeom& g) {
+        rows = smem_warp;
+        xw = smem_warp + NIN * kStripRB * ROWSTRIDE;
+        rows_s = (uint32_t)__cvta_generic_to_shared(rows);
+        const int lane = threadIdx.x & 31;
+        c0 = cw0 - KG / 2 + (lane & 7);
+        ncm1 = g.n_c - 1; nmm1 = g.n_m - 1; mfirst = m_first; stride_m = g.stride_m;
+    }
+    // lane (l8 = lane % 8, rr = lane / 8) fetches elements e = l8 + 8 i of rows rr and rr + 4; element e lives at
+    // (e % 8) * PITCH + e / 8 = l8 * PITCH + i
+    __device__ __forceinline__ void issue(int b) {
+        const int lane = threadIdx.x & 31, l8 = lane & 7, lrr = lane >> 3;
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             const int r = lrr + 4 * p;
-            int m = m0 - R + b * RB + r;
-            m = max(0, min(m, nmm1));
-            const T* row = in_c + (int64_t)m * a.stride_m;
+            const int m = max(0, min(mfirst + b * kStripRB + r, nmm1));
             const uint32_t dst = rows_s + (uint32_t)((r * ROWSTRIDE + l8 * PITCH) * sizeof(T));
 #pragma unroll
             for (int i = 0; i < NLOAD; ++i) {
                 if (ROWLEN % 8 == 0 || l8 + 8 * i < ROWLEN) {
-                    const int c = max(0, min(l_c0 + 8 * i, ncm1));
-                    cp_async_elem<T>(dst + (uint32_t)(i * sizeof(T)), row + c);
+                    const int c = max(0, min(c0 + 8 * i, ncm1));
+#pragma unroll
+                    for (int q = 0; q < NIN; ++q)
+                        cp_async_elem<T>(dst + (uint32_t)((q * kStripRB * ROWSTRIDE + i) * sizeof(T)), src[q] + (int64_t)m * stride_m + c);
                 }
             }
         }
         cp_async_commit();
-    };
-
-    // gather role: row g_r, block g_b of 8 outputs;  march role: column `lane`;  solve role: one voxel of RB x TX
-    const int g_r = lane >> 2, g_b = lane & 3;
-    const T* g_src = rows + g_r * ROWSTRIDE + g_b;
-    T* g_dst = xw + g_r * kXwRow + g_b * (XB + 1);
-    const T* m_src = xw + lane + lane / 8;
-    T* m_dst = park + ch * TX + 32 * half + lane;
-    // Solve work is handed out in units of 32 voxels (RB * TX / 32 = 16 units per batch).  A block has 18 warps on 4
-    // schedulers (warp % 4): two schedulers run 5 window warps, two run 4.  The lighter schedulers take more solve
-    // units (5 each) than the heavier ones (3 each), which evens out the FP64 work per scheduler.
-    constexpr int NUNITS = RB * TX / 32;
-    int su[2] = {-1, -1};
-    if (NCH == 9) {
-        const int q = warp >> 2, sm = warp & 3;                               // q-th warp of scheduler sm
-        if (sm >= 2) { su[0] = (sm - 2) * 5 + q; if (q == 0) su[1] = (sm - 2) * 5 + 4; }   // 4 warps, 5 units
-        else if (q < 3) su[0] = 10 + sm * 3 + q;                              // 5 warps, 3 units
-    } else {
-        su[0] = warp < NUNITS ? warp : -1;
-        su[1] = warp + 2 * NCH < NUNITS ? warp + 2 * NCH : -1;
     }
-    static_assert(NCH != 9 || NUNITS == 16, "unit table assumes 16 units");
+    // gather with filter f (KF <= KG taps, centred in the loaded halo) of input q (or the product of inputs 0 and 1),
+    // result to xw
+    template <int KF, bool PROD>
+    __device__ __forceinline__ void gather(const Taps<T, KF>& f, int q) {
+        constexpr int XB = kStripXB, OFF = (KG - KF) / 2;
+        const int lane = threadIdx.x & 31, g_r = lane >> 2, g_b = lane & 3;
+        const T* s0 = rows + (q * kStripRB + g_r) * ROWSTRIDE + g_b;
+        T ga[XB];
+#pragma unroll
+        for (int i = 0; i < XB; ++i) ga[i] = T(0);
+#pragma unroll
+        for (int mm = OFF; mm < XB + KF - 1 + OFF; ++mm) {
+            T v = s0[(mm & 7) * PITCH + (mm >> 3)];
+            if (PROD) v *= s0[kStripRB * ROWSTRIDE + (mm & 7) * PITCH + (mm >> 3)];
+#pragma unroll
+            for (int i = 0; i < XB; ++i) {
+                const int k = mm - OFF - i;
+                if (k >= 0 && k < KF) ga[i] = fma(f.w[k], v, ga[i]);
+            }
+        }
+        T* d = xw + g_r * kXwRow + g_b * (XB + 1);
+#pragma unroll
+        for (int i = 0; i < XB; ++i) d[i] = ga[i];
+    }
+    __device__ __forceinline__ T gathered(int r) const {
+        const int lane = threadIdx.x & 31;
+        return xw[r * kXwRow + lane + lane / 8];
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Gradient stage.  Roles (one warp each, independent):
+//   0  in dt0: gather G_x, march G_y                      -> out0            (dt before the z pass / dt in 2D)
+//   1  in ic : gather S_x, march D_y -> out1 (dy path) and, in 3D, march S_y -> out3 (dz path)
+//   2  in ic : gather D_x, march S_y                      -> out2            (dx path)
+template <typename T, int KR, int KS>
+struct GradStripArgs {
+    StripGeom g;
+    Taps<T, KR> fG, fD;
+    Taps<T, KS> fS;
+    const T* dt0; const T* ic;
+    T* out[4];              // out[3] == nullptr in 2D
+};
+
+template <typename T, int KR>
+constexpr size_t grad_strip_smem(int wpb) { return (size_t)wpb * StripStage<T, KR, 1>::elems * sizeof(T); }
+
+// One role.  Each role is its own kernel instantiation: dispatched inside one kernel the three bodies get a merged
+// register allocation of 228 registers (8 warps per SM); separately they need 56-95.
+template <typename T, int KR, int KS, int P, int ROLE>
+__device__ __forceinline__ void strip_grad_body(const GradStripArgs<T, KR, KS>& a, T* smem_warp, int strip, int chunk, int o) {
+    constexpr int RB = kStripRB, R = KR / 2, RS = KS / 2;
+    constexpr int KGATHER = ROLE == 1 ? KS : KR;            // taps of the x filter
+    constexpr int KA = ROLE == 2 ? KS : KR;                 // taps of the (first) y filter
+    constexpr int lagA = R + KA / 2;                        // the stream with radius rf completes row m0 + s - R - rf
+    using Stage = StripStage<T, KR, 1>;
+    const StripGeom& g = a.g;
+    const int lane = threadIdx.x & 31;
+    const int cw0 = strip * 32;
+    const int m0 = chunk * g.chunk;
+    const int nout = min(m0 + g.chunk, g.n_m) - m0;
+    const int nsteps = (nout + 2 * R + P - 1) / P * P;
+    const unsigned nvalid = (cw0 + lane < g.n_c) ? (unsigned)nout : 0u;
+
+    Stage st;
+    st.init(smem_warp, cw0, m0 - R, g);
+    st.src[0] = (ROLE == 0 ? a.dt0 : a.ic) + (int64_t)o * g.stride_o;
+    const int64_t obase = (int64_t)o * g.stride_o + cw0 + lane;
+    T* const oA = a.out[ROLE == 0 ? 0 : (ROLE == 1 ? 1 : 2)] + obase;
+    T* const oB = (ROLE == 1 && a.out[3]) ? a.out[3] + obase : nullptr;   // second stream of role 1: S_y (3D only)
+    const Taps<T, KR>& fyA = ROLE == 0 ? a.fG : a.fD;                      // y filter of roles 0 and 1
+
+    T accA[P], accB[ROLE == 1 ? P : 1];
+#pragma unroll
+    for (int i = 0; i < P; ++i) accA[i] = T(0);
+#pragma unroll
+    for (int i = 0; i < (ROLE == 1 ? P : 1); ++i) accB[i] = T(0);
+
+    st.issue(0);
+    int b = 0;
+#pragma unroll 1
+    for (int s0 = 0; s0 < nsteps; s0 += P) {
+#pragma unroll
+        for (int bi = 0; bi < P / RB; ++bi, ++b) {
+            cp_async_wait<0>();
+            __syncwarp();
+            if (ROLE == 0) st.template gather<KR, false>(a.fG, 0);
+            else if (ROLE == 1) st.template gather<KS, false>(a.fS, 0);
+            else st.template gather<KR, false>(a.fD, 0);
+            __syncwarp();
+            st.issue(b + 1);
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int ph = bi * RB + r;
+                const int s = s0 + ph;
+                const T v = st.gathered(r);
+                T resA;
+                if (ROLE == 2) resA = ring_push<T, KS, P>(accA, a.fS, v, ph);
+                else resA = ring_push<T, KR, P>(accA, fyA, v, ph);
+                if ((unsigned)(s - lagA) < nvalid) oA[(int64_t)(m0 + s - lagA) * g.stride_m] = resA;
+                if (ROLE == 1) {
+                    const T resB = ring_push<T, KS, P>(*reinterpret_cast<T(*)[P]>(accB), a.fS, v, ph);
+                    if (oB && (unsigned)(s - R - RS) < nvalid) oB[(int64_t)(m0 + s - R - RS) * g.stride_m] = resB;
+                }
+            }
+            __syncwarp();                                                     // gathered rows consumed before the next gather
+        }
+    }
+    (void)KGATHER;
+    cp_async_wait<0>();
+}
+
+template <typename T, int KR, int KS, int P, int ROLE, int WPB>
+__global__ void __launch_bounds__(WPB * 32) strip_grad(const GradStripArgs<T, KR, KS> a) {
+    static_assert(P >= KR && KR >= KS && P % kStripRB == 0, "bad unroll period");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const StripGeom& g = a.g;
+    int64_t task = (int64_t)blockIdx.x * WPB + warp;
+    const int nstrips = (g.n_c + 31) / 32;
+    if (task >= (int64_t)nstrips * g.n_chunks * g.n_o) return;
+    const int strip = (int)(task % nstrips); task /= nstrips;
+    const int chunk = (int)(task % g.n_chunks);
+    const int o = (int)(task / g.n_chunks);
+    strip_grad_body<T, KR, KS, P, ROLE>(a, reinterpret_cast<T*>(smem_raw) + warp * StripStage<T, KR, 1>::elems, strip, chunk, o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Window x pass + y pass + solve.  A block has NCH * NHALF warps: warp (channel ch, half h) owns columns
+// [cs0 + 32 h, +32) of channel ch.  After gather and march a completed row is parked in shared memory; ONE block
+// barrier per batch, then the voxels of the RB x TX batch are solved (calc_flow.py:337-357 / 154-168) in units of 32
+// voxels handed to the warps so that the FP64 work per scheduler (warp % 4) is even.  The park is double-buffered:
+// warps may run a batch apart, so the latency-bound solve of one warp overlaps the FMA-bound gather/march of others.
+// PROD (2D): the inputs are the gradient volumes and the products are formed in the gather (calc_flow.py:133-141).
+template <typename T, int K>
+struct StripArgs {
+    StripGeom g;
+    Taps<T, K> f;
+    const T* in[4];         // !PROD: in[0] = channel-major window sums of the z pass; PROD: gradients {dt, dx, dy, -}
+    T* vx; T* vy; T* vz; T* rel;
+};
+
+template <int NCH, int NHALF> constexpr int strip_parkrow() { return NCH * NHALF * 32 + 2; }
+template <typename T, int K, int NCH, int NHALF, bool PROD>
+constexpr size_t strip_smem() {
+    return (size_t)(NCH * NHALF * StripStage<T, K, PROD ? 2 : 1>::elems + 2 * kStripRB * strip_parkrow<NCH, NHALF>()) * sizeof(T);
+}
+
+// solve units (32 voxels each) of warp `warp`; returns how many
+template <int NCH, int NHALF>
+__device__ __forceinline__ int solve_units(int warp, int (&su)[4]) {
+    const int q = warp >> 2, sm = warp & 3;            // q-th warp of scheduler sm
+    int n = 0;
+    if (NCH == 9 && NHALF == 2) {                      // 18 warps (5,5,4,4), 16 units: 3,3,5,5
+        if (sm >= 2) { su[n++] = (sm - 2) * 5 + q; if (q == 0) su[n++] = (sm - 2) * 5 + 4; }
+        else if (q < 3) su[n++] = 10 + sm * 3 + q;
+    } else if (NCH == 9 && NHALF == 1) {               // 9 warps (3,2,2,2), 8 units: 0,3,3,2
+        if (sm == 1) { su[n++] = q; if (q == 0) su[n++] = 2; }
+        else if (sm == 2) { su[n++] = 3 + q; if (q == 0) su[n++] = 5; }
+        else if (sm == 3) su[n++] = 6 + q;
+    } else if (NCH == 5 && NHALF == 2) {               // 10 warps (3,3,2,2), 16 units: 0,0,8,8
+        if (sm >= 2) for (int i = 0; i < 4; ++i) su[n++] = (sm - 2) * 8 + q * 4 + i;
+    } else {                                           // generic: round robin
+        for (int u = warp; u < kStripRB * NHALF; u += NCH * NHALF) if (n < 4) su[n++] = u;
+    }
+    return n;
+}
+
+template <typename T, int K, int P, int NCH, int NHALF, bool PROD>
+__global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const StripArgs<T, K> a) {
+    constexpr int RB = kStripRB, R = K / 2, TX = 32 * NHALF;
+    constexpr int PARKROW = strip_parkrow<NCH, NHALF>();
+    static_assert(P >= K && P % RB == 0, "unroll period must cover the taps and be a multiple of the batch");
+    static_assert(NCH * NHALF >= 4 || true, "");
+    using Stage = StripStage<T, K, PROD ? 2 : 1>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = warp % NCH, half = warp / NCH;
+    T* park = smem + NCH * NHALF * Stage::elems;                             // [2][RB][PARKROW], shared by the block
+    const StripGeom& g = a.g;
+
+    int task = blockIdx.x;
+    const int nstrips = (g.n_c + TX - 1) / TX;
+    const int strip = task % nstrips; task /= nstrips;
+    const int chunk = task % g.n_chunks;
+    const int o = task / g.n_chunks;
+    const int cs0 = strip * TX;                                              // first column of the block's strip
+    const int m0 = chunk * g.chunk;
+    const int nout = min(m0 + g.chunk, g.n_m) - m0;
+    const int nsteps = (nout + 2 * R + P - 1) / P * P;                       // whole unroll periods
+
+    Stage st;
+    st.init(smem + warp * Stage::elems, cs0 + 32 * half, m0 - R, g);
+    if (PROD) {
+        // channel -> gradient pair {xx,xy,yy,tx,ty}; a.in = {dt, dx, dy}
+        const int ia = (ch == 2 || ch == 4) ? 2 : 1;
+        const int ib = ch == 0 ? 1 : (ch <= 2 ? 2 : 0);
+        st.src[0] = a.in[ia] + (int64_t)o * g.stride_o;
+        st.src[PROD ? 1 : 0] = a.in[ib] + (int64_t)o * g.stride_o;
+    } else {
+        st.src[0] = a.in[0] + (int64_t)o * g.stride_o + (int64_t)ch * g.vol;
+    }
+    T* const m_dst = park + ch * TX + 32 * half + lane;
+    int su[4] = {-1, -1, -1, -1};
+    const int nsu = solve_units<NCH, NHALF>(warp, su);
+
     T acc[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) acc[i] = T(0);
 
-    issue_batch(0);
+    st.issue(0);
     int b = 0;
 #pragma unroll 1
     for (int s0 = 0; s0 < nsteps; s0 += P) {
@@ -144,59 +301,35 @@ __global__ void __launch_bounds__(NCH * kStripTX, 1) strip_window_solve(const St
         for (int bi = 0; bi < P / RB; ++bi, ++b) {
             cp_async_wait<0>();
             __syncwarp();                                                     // this warp's rows of batch b have landed
-            // ---------------- gather along c
-            {
-                T ga[XB];
-#pragma unroll
-                for (int i = 0; i < XB; ++i) ga[i] = T(0);
-#pragma unroll
-                for (int mm = 0; mm < XB + K - 1; ++mm) {
-                    const T v = g_src[(mm & 7) * PITCH + (mm >> 3)];
-#pragma unroll
-                    for (int i = 0; i < XB; ++i) {
-                        const int k = mm - i;
-                        if (k >= 0 && k < K) ga[i] = fma(a.f.w[k], v, ga[i]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < XB; ++i) g_dst[i] = ga[i];
-            }
+            st.template gather<K, PROD>(a.f, 0);
             __syncwarp();                                                     // gathered rows visible; input rows free
-            issue_batch(b + 1);                                               // prefetch (clamped addresses: always valid)
-            // ---------------- march along m: output j = s - 2R lives in park row j mod RB of buffer b & 1
+            st.issue(b + 1);                                                  // prefetch (clamped addresses: always valid)
+            // ---------------- march along y: output j = s - 2R lives in park row j mod RB of buffer b & 1
             {
                 T* pk = m_dst + (b & 1) * RB * PARKROW;
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
-                    const T v = m_src[r * kXwRow];
-                    const T res = ring_push<T, K, P>(acc, a.f, v, bi * RB + r);
+                    const T res = ring_push<T, K, P>(acc, a.f, st.gathered(r), bi * RB + r);
                     constexpr int kBias = (2 * R + RB - 1) / RB * RB;
                     pk[((r + kBias - 2 * R) % RB) * PARKROW] = res;
                 }
             }
             __syncthreads();                                                  // one batch of outputs parked by all channels
-            // ---------------- solve: outputs j0 .. j0 + RB - 1 of batch b
-#pragma unroll
-            for (int ui = 0; ui < 2; ++ui) {
-                if (su[ui] < 0) continue;                                     // warp-uniform
-                const int v = su[ui] * 32 + lane;                             // voxel of the RB x TX batch
-                const int s_i = TR ? (v % RB) : (v / TX);                     // output row within the batch
-                const int s_col = TR ? (v / RB) : (v % TX);
+            // ---------------- solve the RB x TX outputs of batch b
+#pragma unroll 1
+            for (int ui = 0; ui < nsu; ++ui) {
+                const int v = su[ui] * 32 + lane;                             // voxel of the batch: row v / TX, column v % TX
+                const int s_i = v / TX, s_col = v % TX;
                 const int s_c = cs0 + s_col;
                 const int j = b * RB - 2 * R + s_i;
-                if (j >= 0 && j < nout && s_c < a.n_c) {
+                if (j >= 0 && j < nout && s_c < g.n_c) {
                     const int prow = ((j % RB) + RB) % RB;
                     const T* qv = park + ((b & 1) * RB + prow) * PARKROW + s_col;
-                    const int64_t idx = TR ? ((int64_t)o * a.stride_o + (int64_t)s_c * a.n_m + (m0 + j))
-                                           : ((int64_t)o * a.stride_o + (int64_t)(m0 + j) * a.stride_m + s_c);
+                    const int64_t idx = (int64_t)o * g.stride_o + (int64_t)(m0 + j) * g.stride_m + s_c;
                     if (NCH == 9) {
-#ifdef OF3D_EXP_NOSOLVE
-                        Flow3 rr; rr.vx = qv[0] + qv[TX] + qv[2 * TX]; rr.vy = qv[3 * TX] + qv[4 * TX]; rr.vz = qv[5 * TX] + qv[6 * TX]; rr.rel = qv[7 * TX] + qv[8 * TX];
-#else
                         const Flow3 rr = solve3<false>((double)qv[0], (double)qv[TX], (double)qv[2 * TX], (double)qv[3 * TX],
                                                        (double)qv[4 * TX], (double)qv[5 * TX], (double)qv[6 * TX],
                                                        (double)qv[7 * TX], (double)qv[8 * TX]);
-#endif
                         a.vx[idx] = (T)rr.vx; a.vy[idx] = (T)rr.vy; a.vz[idx] = (T)rr.vz; a.rel[idx] = (T)rr.rel;
                     } else {
                         const Flow2 rr = solve2<false>((double)qv[0], (double)qv[TX], (double)qv[2 * TX], (double)qv[3 * TX],
