@@ -249,3 +249,44 @@ def test_synth_blobs_kernel_statistics():
     torch.cuda.synchronize()
     _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, one.data_ptr(), 1, 16, 64, 96, 11, 0, 1234), 'synth')
     assert np.array_equal(one.cpu().numpy()[0], buf.cpu().numpy()[1])
+
+
+# ------------------------------------------------------------------ BASELINE full sizes (size-independent properties)
+def _device_window(shape, seed):
+    """Synthetic uint16 window generated on the device (of3d_synth_blobs), returned as an int16-typed CUDA tensor."""
+    import torch
+    from opticalflow3d_dev_b200 import _lib
+    ctx = _lib.get_context(0)
+    buf = torch.empty(shape, dtype=torch.uint16, device='cuda')
+    torch.cuda.synchronize()
+    nt, nz = shape[0], (shape[1] if len(shape) == 4 else 1)
+    _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, buf.data_ptr(), nt, nz, shape[-2], shape[-1], 0, 0, seed), 'synth')
+    return buf
+
+
+@pytest.mark.parametrize('shape,sig,ndim', [
+    ((7, 128, 1024, 1024), (3, 1, 4), 3),        # cfg4: one window of the 1024x1024x128 stack
+    ((7, 2048, 2048), (1.5, 1, 4), 2),           # cfg2: one 2048x2048 frame
+    ((13, 64, 512, 512), (3, 2, 6), 3),          # cfg3
+])
+def test_full_size_fast_path_matches_generic_kernels(shape, sig, ndim):
+    """At full BASELINE sizes the oracle is too slow; the marching/strip kernels are checked against the generic
+    one-output-per-thread kernels (an independent implementation that is itself bit-exact against the reference
+    on the goldens in exact mode), plus basic sanity of the reliability."""
+    import torch
+    cf = _cf()
+    win = _device_window(shape, 77)
+    fn = cf.calc_flow3D if ndim == 3 else cf.calc_flow2D
+    kw = dict(rel_dtype='float64') if ndim == 3 else {}
+    fast = fn(win, *sig, **kw)
+    gen = fn(win, *sig, generic=True, **kw)
+    vmax = max(float(g.abs().max()) for g in gen[:-1])
+    assert vmax > 1e-3
+    for f, g in zip(fast[:-1], gen[:-1]):
+        assert torch.isfinite(f).all()
+        assert float((f - g).abs().max()) <= 1e-9 * vmax
+    lam = float(gen[-1].abs().max())
+    assert float((fast[-1] - gen[-1]).abs().max()) <= 1e-10 * lam
+    assert float(fast[-1].min()) > -1e-9 * lam          # smallest eigenvalue of a PSD window tensor
+    del fast, gen, win
+    torch.cuda.empty_cache()
