@@ -113,7 +113,27 @@ struct GenericPipe {
 
     template <typename Tin>
     void temporal(const FramePtrs& fp, T* ic, T* dt0) {
-        temporal_generic<Tin, T, EXACT><<<grid_for(c, s.n()), 256, 0, c->stream>>>(fp, fT, ic, dt0, s.n());
+        const int64_t n = s.n();
+        if (!EXACT) {
+            // 16-byte vector path when every frame (and the outputs) is 16-byte aligned; scalar kernel for the tail
+            constexpr int VEC = 16 / sizeof(Tin);
+            bool aligned = (reinterpret_cast<uintptr_t>(ic) | reinterpret_cast<uintptr_t>(dt0)) % 16 == 0;
+            for (int k = 0; k < fT.n; ++k) aligned = aligned && reinterpret_cast<uintptr_t>(fp.p[k]) % 16 == 0;
+            const int64_t nvec = aligned ? n / VEC : 0;
+            if (nvec > 0) {
+                temporal_vec<Tin, T><<<grid_for(c, nvec), 256, 0, c->stream>>>(fp, fT, ic, dt0, nvec);
+                c->launches++;
+                const int64_t done = nvec * VEC;
+                if (done < n) {
+                    FramePtrs tail = fp;
+                    for (int k = 0; k < fT.n; ++k) tail.p[k] = reinterpret_cast<const Tin*>(fp.p[k]) + done;
+                    temporal_generic<Tin, T, false><<<grid_for(c, n - done), 256, 0, c->stream>>>(tail, fT, ic + done, dt0 + done, n - done);
+                    c->launches++;
+                }
+                return;
+            }
+        }
+        temporal_generic<Tin, T, EXACT><<<grid_for(c, n), 256, 0, c->stream>>>(fp, fT, ic, dt0, n);
         c->launches++;
     }
 
