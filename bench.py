@@ -36,6 +36,9 @@ WORKLOADS = {
     'cfg2': dict(shape=(31, 2048, 2048), sig=(1.5, 1, 4)),
     'cfg3': dict(shape=(31, 64, 512, 512), sig=(3, 2, 6)),
     'cfg4': dict(shape=(61, 128, 1024, 1024), sig=(3, 1, 4)),   # the configuration the metric is quoted on
+    # one 19-frame window of a 2048x2048x512 volume: too large for one GPU, sharded by z-slab with an NCCL halo
+    # exchange (needs --gpus >= 4 in fp64, >= 2 in fp32)
+    'cfg5': dict(shape=(19, 512, 2048, 2048), sig=(3, 3, 8), zslab=True),
 }
 METRIC = 'output voxels/s (vx,vy,vz,rel) 1024x1024x128 stack'
 UNIT = 'voxels/s'
@@ -47,6 +50,29 @@ def peaks():
             return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     except Exception:
         return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def fma_peak(precision):
+    """Measured CUDA-core FMA issue peak of this pool's B200 (tools/fma_peak.cu -> profiles/r01_fma_peak.json), TFMA/s."""
+    best = {'fp64': 17.0, 'fp32': 36.2}          # values recorded in DESIGN.md; refreshed from the profile if present
+    try:
+        for line in open(os.path.join(ROOT, 'profiles', 'r01_fma_peak.json')):
+            d = json.loads(line)
+            if d.get('pipe') in best:
+                best[d['pipe']] = max(best[d['pipe']], float(d['tfma_per_s']))
+    except Exception:
+        pass
+    return best[precision]
+
+
+def measured_traffic(workload, precision):
+    """DRAM bytes per output voxel of the whole per-timepoint pipeline, from the committed ncu launch lists
+    (profiles/r01_traffic.json: sum of dram__bytes_read.sum + dram__bytes_write.sum over the launches of one timepoint)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as fh:
+            return json.load(fh).get('%s_%s' % (workload, precision))
+    except Exception:
+        return None
 
 
 def alg_bytes_per_voxel(sig, ndim, precision, in_itemsize=2):
@@ -187,6 +213,84 @@ def reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def zslab_arm(args, rank, world, local_rank):
+    """cfg5: ONE output timepoint of a volume sharded by z-slab; every step = temporal stage on the owned planes,
+    NCCL halo exchange of (ic, dt0) with the two neighbours, spatial stages on the extended slab, crop."""
+    import torch
+    import torch.distributed as dist
+    from opticalflow3d_dev_b200.build import build_library
+    if rank == 0:
+        build_library()
+    if world < 2:
+        raise SystemExit('workload cfg5 is z-slab sharded and needs --gpus >= 2')
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dist.barrier()
+    from opticalflow3d_dev_b200 import _lib, multigpu
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    w = WORKLOADS[args.workload]
+    nt, nz, ny, nx = w['shape']
+    sig = w['sig']
+    z0, z1 = multigpu.shard_timepoints(nz, world)[rank]
+    ctx = _lib.get_context(local_rank)
+    frames = torch.empty((nt, z1 - z0, ny, nx), dtype=torch.uint16, device=dev)
+    torch.cuda.synchronize()
+    _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, frames.data_ptr(), nt, z1 - z0, ny, nx, 0, z0, 1000 + 5), 'synth')
+
+    def step():
+        out = multigpu.calc_flow3D_zslab(frames, *sig, nz_total=nz, precision=args.precision)
+        return out
+
+    def barrier():
+        ctx.sync(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        o = step(); del o
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        o = step(); del o
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    lsum = torch.tensor([float(ctx.launch_count() - l0)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        vol = nz * ny * nx
+        value = vol * args.steps / (float(tmax.item()) * 1e-3)
+        peak, peak_src = peaks()
+        bpv = alg_bytes_per_voxel(sig, 3, args.precision)
+        fma = alg_fma_per_voxel(sig, 3)
+        fpk = fma_peak(args.precision)
+        halo = multigpu.halo_planes(sig[0], sig[2])
+        es = 8 if args.precision == 'fp64' else 4
+        line = {
+            'metric': 'output voxels/s (vx,vy,vz,rel) 2048x2048x512 volume, z-slab sharded', 'value': value, 'unit': UNIT,
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(tmax.item()) / args.steps,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f64' if args.precision == 'fp64' else 'f32', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'shape': list(w['shape']), 'sigmas': list(sig), 'input_dtype': 'uint16',
+                       'sharding': 'z-slab, %d halo planes of (ic, dt0) exchanged with each neighbour over NCCL' % halo,
+                       'halo_bytes_per_rank_per_step': int(2 * 2 * halo * ny * nx * es)},
+            'roofline': {'bound': 'hbm', 'achieved': value * bpv / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
+                         'frac': value * bpv / 1e9 / world / peak, 'traffic': None, 'peak_source': peak_src,
+                         'alg_bytes_per_voxel': bpv,
+                         'fp_pipe': {'alg_fma_per_voxel': fma, 'achieved_tfma_per_s': value * fma / 1e12 / world,
+                                     'peak_tfma_per_s': fpk, 'frac': value * fma / 1e12 / world / fpk}},
+            'clocks': clocks, 'gpu_launches': int(lsum.item()), 'e2e': None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def gpu_arm(args, rank, world, local_rank):
     import ctypes as C
     import torch
@@ -311,6 +415,8 @@ def gpu_arm(args, rank, world, local_rank):
     bpv = alg_bytes_per_voxel(sig, ndim, args.precision)
     ach = value * bpv / 1e9 / world                             # per-GPU algorithmic GB/s
     fma = alg_fma_per_voxel(sig, ndim)
+    fpk = fma_peak(args.precision)
+    tr = measured_traffic(args.workload, args.precision)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
@@ -319,10 +425,14 @@ def gpu_arm(args, rank, world, local_rank):
                    'output_timepoints_per_step': len(outs_all), 'sharding': 'output timepoint, no collective',
                    'l2': 'inputs+intermediates per timepoint (>= %.1f GB) exceed the 126 MB L2' % (kt * vol * 2 / 1e9),
                    'kernels': 'generic' if args.generic else 'default'},
-        'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
-                     'peak_source': peak_src, 'alg_bytes_per_voxel': bpv, 'per': 'GPU, whole per-timepoint pipeline',
+        'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                     'traffic': (tr['bytes_per_voxel'] * vol if tr else None),
+                     'peak_source': peak_src, 'alg_bytes_per_voxel': bpv,
+                     'alg_bytes_per_launch': bpv * vol, 'launch': 'one output timepoint = the whole pipeline (%s kernels)' %
+                     (tr['kernels'] if tr else 'several'), 'traffic_bytes_per_voxel': (tr['bytes_per_voxel'] if tr else None),
                      'fp_pipe': {'alg_fma_per_voxel': fma, 'achieved_tfma_per_s': value * fma / 1e12 / world,
-                                 'note': 'binding roof is the CUDA-core FMA pipe, see DESIGN.md'}},
+                                 'peak_tfma_per_s': fpk, 'frac': value * fma / 1e12 / world / fpk,
+                                 'note': 'the binding roof is the CUDA-core FMA pipe (measured peak, tools/fma_peak.cu); see DESIGN.md'}},
         'clocks': clocks, 'gpu_launches': int(lsum.item()), 'e2e': e2e,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -353,7 +463,10 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-voxels', type=int, default=400_000, help='voxels per core per CPU step')
     ap.add_argument('--cpu-cores', type=int, default=None)
+    ap.add_argument('--shape', default=None, help='override the workload shape, e.g. 19,128,512,512 (debug)')
     args = ap.parse_args()
+    if args.shape:
+        WORKLOADS[args.workload] = dict(WORKLOADS[args.workload], shape=tuple(int(v) for v in args.shape.split(',')))
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':
@@ -364,6 +477,9 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
                '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 1000)] + sys.argv
         os.execv(sys.executable, cmd)
+    if WORKLOADS[args.workload].get('zslab'):
+        zslab_arm(args, rank, world, local_rank)
+        return
     gpu_arm(args, rank, world, local_rank)
     _finish(world)
 
