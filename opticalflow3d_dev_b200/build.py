@@ -24,7 +24,7 @@ def _newest_source_mtime():
     m = 0.0
     for d in (CSRC, os.path.join(os.path.dirname(PKG), 'include')):
         for f in os.listdir(d):
-            if f.endswith(('.cu', '.cuh', '.h')):
+            if f.endswith(('.cu', '.cuh', '.h', '.inc')):
                 m = max(m, os.path.getmtime(os.path.join(d, f)))
     return m
 
