@@ -382,32 +382,58 @@ def gpu_arm(args, rank, world, local_rank):
     value = total_vox / (ms_total * 1e-3)
     ctx.set_async(False)
 
-    # ---- end-to-end through the drop-in Python call with host (pinned) buffers
+    # ---- end-to-end with HOST buffers, copies inside the timed region, two public entry points:
+    #   stream : FlowStream (the engine under process_flow): every frame uploaded once from pinned memory, results
+    #            copied back to pinned memory while the next window computes  -> the headline e2e
+    #   call   : the synchronous drop-in calc_flow3D(host window) -> host arrays (re-uploads the whole window per call)
     e2e = None
     if not args.no_e2e:
+        from opticalflow3d_dev_b200.timelapse import FlowStream
         n_e2e = max(1, min(args.e2e_timepoints, len(mine))) if mine else 0
         np_odt = np.float64 if args.precision == 'fp64' else np.float32
+        call_rate = None
         if n_e2e:
-            hwin = _lib.pinned_empty((n_e2e + 2 * rt,) + tuple(sp), np.uint16)
-            hwin[...] = frames[:n_e2e + 2 * rt].reshape(hwin.shape).cpu().numpy().view(np.uint16)
+            nfr = n_e2e + 2 * rt + 2                             # frames fed to the stream: 2 warm-up windows + n_e2e timed
+            nfr = min(nfr, nloc)
+            hfr = _lib.pinned_empty((nfr,) + tuple(sp), np.uint16)
+            hfr[...] = frames[:nfr].reshape(hfr.shape).cpu().numpy().view(np.uint16)
+            eng = FlowStream(tuple(sp), np.uint16, sig, precision=args.precision, device=local_rank)
+            n_warm = nfr - n_e2e                                 # pushes before the timed region (fills the ring + warm-up)
+            for i in range(n_warm):
+                eng.push(hfr[i], pinned=True)
+            eng.flush()
+        barrier()
+        t0 = time.perf_counter()
+        if n_e2e:
+            b0, b1 = eng.h2d_bytes, eng.d2h_bytes
+            for i in range(n_warm, nfr):
+                eng.push(hfr[i], pinned=True)
+            eng.flush()
+        dt = time.perf_counter() - t0
+        if n_e2e:
+            h2d, d2h = eng.h2d_bytes - b0, eng.d2h_bytes - b1
+            eng.close()
+            del eng
+            # the synchronous per-window call, for comparison
             hout = tuple(_lib.pinned_empty(tuple(sp), np_odt) for _ in range(ndim + 1))
             fn = calc_flow3D if ndim == 3 else calc_flow2D
             kw = dict(precision=args.precision, device=local_rank, out=hout, generic=args.generic)
-            fn(hwin[0:kt], *sig, **kw)                              # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(n_e2e):
-            fn(hwin[i:i + kt], *sig, **kw)
-        ctx.sync()
-        dt = time.perf_counter() - t0
+            fn(hfr[0:kt], *sig, **kw)
+            tc = time.perf_counter()
+            fn(hfr[1:1 + kt], *sig, **kw)
+            call_rate = vol / (time.perf_counter() - tc)
+        else:
+            h2d = d2h = 0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        nn = torch.tensor([float(n_e2e)], dtype=torch.float64, device=dev)
+        nn = torch.tensor([float(n_e2e), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(nn, op=dist.ReduceOp.SUM)
-        e2e = {'value': float(nn.item()) * vol / float(tt.item()), 'unit': UNIT,
-               'h2d_bytes_per_step': int(kt * vol * 2 * nn.item()),
-               'd2h_bytes_per_step': int((ndim + 1) * vol * np.dtype(np_odt).itemsize * nn.item()),
-               'timepoints': int(nn.item()), 'api': 'calc_flow%dD(host ndarray window) -> host ndarrays (pinned)' % ndim}
+        e2e = {'value': float(nn[0].item()) * vol / float(tt.item()), 'unit': UNIT,
+               'h2d_bytes_per_step': int(nn[1].item()), 'd2h_bytes_per_step': int(nn[2].item()),
+               'timepoints': int(nn[0].item()),
+               'api': 'timelapse.FlowStream.push(host frame) -> host (vx,vy,vz,rel), pinned; the engine under process_flow',
+               'calc_flow_call_value': call_rate,
+               'calc_flow_call_api': 'calc_flow%dD(host ndarray window) -> host ndarrays (pinned), rank 0' % ndim}
 
     if rank != 0:
         return
@@ -458,7 +484,7 @@ def main():
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'fp32'])
     ap.add_argument('--timepoints', type=int, default=None, help='limit the number of output timepoints (debug)')
     ap.add_argument('--generic', action='store_true', help='force the generic kernels')
-    ap.add_argument('--e2e-timepoints', type=int, default=2)
+    ap.add_argument('--e2e-timepoints', type=int, default=6)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-voxels', type=int, default=400_000, help='voxels per core per CPU step')

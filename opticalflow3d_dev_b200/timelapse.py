@@ -145,90 +145,180 @@ def process_flow(imDir, imName, fileType="SequenceT", spatialDimensions=3, xyzSi
         say(str(datetime.now()) + ' - No data will be saved for frame ' + str(hh) + ' to avoid edge effects')
 
 
+class FlowStream:
+    """Streaming engine for a time-lapse on one GPU: what the reference's loop at calc_flow.py:512-534 becomes when
+    every frame is uploaded once and copies overlap compute.
+
+        eng = FlowStream(spatial_shape, dtype, (xyzSig, tSig, wSig), precision='fp64', device=0)
+        for t, frame in enumerate(frames):            # host arrays, in time order
+            done = eng.push(frame)                    # -> None or (centre_index, (vx, vy[, vz], rel)) of an EARLIER window
+        done = eng.flush()                            # the last pending result
+
+    * a device-resident ring holds the last Kt frames (Kt = number of temporal taps); `push` copies the new frame
+      through pinned staging on a copy stream;
+    * when a window is complete, of3d_flow_frames is enqueued on the library's stream (asynchronous mode) into one of
+      two device output sets, and the device->host copy of that set runs on a second copy stream while the NEXT
+      window computes;
+    * results are returned one call later as views of pinned host buffers; three host buffer sets rotate, so a
+      returned result stays valid during the next TWO calls of push() -- copy it or finish writing it before the third.
+    """
+
+    def __init__(self, spatial_shape, dtype, sigmas, precision='fp64', device=None):
+        import torch
+        self.torch = torch
+        self.sp = tuple(int(v) for v in spatial_shape)
+        self.ndim = len(self.sp)
+        if self.ndim not in (2, 3):
+            raise ValueError('spatial_shape must be (Ny,Nx) or (Nz,Ny,Nx)')
+        self.in_dt = np.dtype(dtype)
+        if self.in_dt not in _lib.DTYPE_CODES:
+            raise TypeError('unsupported frame dtype %s' % self.in_dt)
+        self.code = _lib.DTYPE_CODES[self.in_dt]
+        self.dev = (int(os.environ.get('OF3D_DEVICE', os.environ.get('LOCAL_RANK', 0))) if device is None else int(device))
+        self.ctx = _lib.get_context(self.dev)
+        self.taps, self._keep = _lib.make_taps(flow_taps(*sigmas))
+        self.kt = self._keep[3].size
+        self.precision = precision
+        self.prec = _lib.FP64 if precision == 'fp64' else _lib.FP32
+        self.odt = np.dtype(np.float64 if precision == 'fp64' else np.float32)
+        self.nvox = int(np.prod(self.sp))
+        self.nout = self.ndim + 1
+        tdev = torch.device('cuda', self.dev)
+        self.tdev = tdev
+        fbytes = self.nvox * self.in_dt.itemsize
+        self.ring = torch.empty((self.kt, fbytes), dtype=torch.uint8, device=tdev)       # frame t lives in slot t % kt
+        self.stage = [_lib.pinned_empty(self.sp, self.in_dt) for _ in range(2)]
+        self.stage_ev = [None, None]
+        self.d_out = [[torch.empty(self.nvox * self.odt.itemsize, dtype=torch.uint8, device=tdev) for _ in range(self.nout)]
+                      for _ in range(2)]
+        self.h_out = [[_lib.pinned_empty(self.sp, self.odt) for _ in range(self.nout)] for _ in range(3)]
+        self.s_in = torch.cuda.Stream(device=tdev)
+        self.s_out = torch.cuda.Stream(device=tdev)
+        self.s_lib = torch.cuda.ExternalStream(self.ctx.stream, device=tdev)
+        self.ctx.set_async(True)
+        self.t = 0                    # frames pushed so far
+        self.nwin = 0                 # windows launched so far
+        self.pending = None           # (centre, slot, done_event) of the window whose result is not yet returned
+        self.slot_free_ev = [None, None]   # compute may overwrite d_out[slot] after its D2H finished
+        self.ring_free_ev = None           # upload may overwrite a ring slot after the compute that read it
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _collect(self):
+        if self.pending is None:
+            return None
+        centre, hslot, ev = self.pending
+        ev.synchronize()
+        self.pending = None
+        return centre, tuple(self.h_out[hslot])
+
+    def push(self, frame, pinned=False):
+        """Feed the next frame (host array).  pinned=True: `frame` already lives in page-locked memory (e.g.
+        _lib.pinned_empty), has the stream's dtype, is C-contiguous and stays untouched until the next push -- it is
+        then uploaded directly, without the staging copy."""
+        torch = self.torch
+        a = np.asarray(frame)
+        if a.shape != self.sp:
+            raise ValueError('frame shape %s, expected %s' % (a.shape, self.sp))
+        k = self.t % 2
+        if pinned and a.dtype == self.in_dt and a.flags.c_contiguous:
+            src = a
+        else:
+            if self.stage_ev[k] is not None:
+                self.stage_ev[k].synchronize()             # pinned staging buffer is free again
+            self.stage[k][...] = a                         # host copy (and dtype conversion) into pinned memory
+            src = self.stage[k]
+        with torch.cuda.stream(self.s_in):
+            if self.ring_free_ev is not None:
+                self.s_in.wait_event(self.ring_free_ev)    # the window that read this ring slot has been computed
+            self.ring[self.t % self.kt].copy_(torch.from_numpy(src.reshape(-1).view(np.uint8)), non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(self.s_in)
+        self.stage_ev[k] = ev
+        self.h2d_bytes += src.nbytes
+        self.t += 1
+        if self.t < self.kt:
+            return None
+        # ---- a window is complete: frames t-kt .. t-1, centre t-1-kt//2
+        done = self._collect()                             # result of the previous window (its D2H overlapped our upload)
+        slot = self.nwin % 2                               # device output set
+        hslot = self.nwin % 3                              # host output set
+        first = self.t - self.kt
+        self.s_lib.wait_event(ev)                          # all uploads so far (same stream order) have landed
+        if self.slot_free_ev[slot] is not None:
+            self.s_lib.wait_event(self.slot_free_ev[slot])
+        ptrs = (C.c_void_p * self.kt)(*[self.ring[(first + i) % self.kt].data_ptr() for i in range(self.kt)])
+        o = [C.c_void_p(x.data_ptr()) for x in self.d_out[slot]]
+        if self.ndim == 2:
+            o = [o[0], o[1], None, o[2]]
+        nz = self.sp[0] if self.ndim == 3 else 1
+        rc = self.ctx.lib.of3d_flow_frames(self.ctx.handle, self.ndim, ptrs, self.code, _lib.DEVICE, nz, self.sp[-2], self.sp[-1],
+                                           C.byref(self.taps), self.prec, 0, o[0], o[1], o[2], o[3], _lib.DEVICE)
+        _lib.check(rc, 'of3d_flow_frames')
+        cev = torch.cuda.Event(); cev.record(self.s_lib)
+        self.ring_free_ev = cev
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(cev)
+            for d, h in zip(self.d_out[slot], self.h_out[hslot]):
+                torch.from_numpy(h.reshape(-1).view(np.uint8)).copy_(d, non_blocking=True)
+                self.d2h_bytes += h.nbytes
+            dev_ = torch.cuda.Event(); dev_.record(self.s_out)
+        self.slot_free_ev[slot] = dev_
+        self.pending = (first + self.kt // 2, hslot, dev_)
+        self.nwin += 1
+        return done
+
+    def flush(self):
+        return self._collect()
+
+    def close(self):
+        self.ctx.sync()
+        self.ctx.set_async(False)
+
+
 def _stream(imDir, fileList, fileType, ndim, dims, sig, NtChunk, NtSlice, starts, savedir, name, precision, device, writers,
             verbose):
-    import torch
     Nt, Nz, Ny, Nx = dims
     src = _FrameSource(imDir, fileList, fileType, Nt, Nz, ndim)
-    first = src.frame(starts[0])
     sp = (Nz, Ny, Nx) if ndim == 3 else (Ny, Nx)
+    first = src.frame(starts[0])
     if first.shape != sp:
         sys.exit('ERROR: frame shape %s does not match the metadata %s' % (first.shape, sp))
-    if first.dtype not in _lib.DTYPE_CODES:
-        first = first.astype(np.float64)
-    in_dt = first.dtype
-    code = _lib.DTYPE_CODES[in_dt]
-    dev = (int(os.environ.get('OF3D_DEVICE', os.environ.get('LOCAL_RANK', 0))) if device is None else int(device))
-    ctx = _lib.get_context(dev)
-    lib = ctx.lib
-    taps, keep = _lib.make_taps(flow_taps(*sig))
-    kt = keep[3].size                                          # temporal taps actually read (<= NtChunk)
-    off = NtSlice - kt // 2                                    # first frame of the window the t-filter touches
-    prec = _lib.FP64 if precision == 'fp64' else _lib.FP32
-    odt = np.float64 if precision == 'fp64' else np.float32
-    nvox = int(np.prod(sp))
-    fbytes = nvox * in_dt.itemsize
-    nout = ndim + 1
-
-    tdev = torch.device('cuda', dev)
-    ring = torch.empty((kt, fbytes), dtype=torch.uint8, device=tdev)              # frame t lives in slot t % kt
-    stage = [_lib.pinned_empty(sp, in_dt) for _ in range(2)]                      # pinned upload staging
-    d_out = [torch.empty(nvox * np.dtype(odt).itemsize, dtype=torch.uint8, device=tdev) for _ in range(nout)]
-    h_out = [[_lib.pinned_empty(sp, odt) for _ in range(nout)] for _ in range(2)]  # double-buffered results
-    pending = [None, None]
-    resident = set()
-    up = 0
+    in_dt = first.dtype if first.dtype in _lib.DTYPE_CODES else np.dtype(np.float64)
+    eng = FlowStream(sp, in_dt, sig, precision=precision, device=device)
+    kt = eng.kt
+    off = NtSlice - kt // 2                                    # first frame of a window the t-filter touches
     names = ['vx', 'vy', 'vz', 'rel'] if ndim == 3 else ['vx', 'vy', 'rel']
-    copy_stream = torch.cuda.Stream(device=tdev)
+    t_start = {}
 
-    def upload(t):
-        nonlocal up
-        a = src.frame(t)
-        if a.dtype != in_dt:
-            a = a.astype(in_dt)
-        buf = stage[up % 2]
-        copy_stream.synchronize()                                                 # staging buffer free again
-        buf[...] = a
-        with torch.cuda.stream(copy_stream):
-            ring[t % kt].copy_(torch.from_numpy(buf.reshape(-1).view(np.uint8)), non_blocking=True)
-        up += 1
-        resident.add(t)
-        resident.discard(t - kt)
-
-    def write_all(arrs, tstr):
+    def write_all(arrs, centre):
+        tstr = str(centre).zfill(4)
         for nm, a in zip(names, arrs):
             out = a
             if ndim == 3 and nm == 'rel' and precision == 'fp64':
                 out = a.astype(np.float32)             # dtype the reference writes (calc_flow.py:355-357, :529)
             tiffio.imwrite(str(savedir / name) + '_' + nm + '_t' + tstr + '.tiff', out, photometric='minisblack')
+        if verbose:
+            print(str(datetime.now()) + ' - Frame ' + str(centre) + ' saved.  Duration: ' + str(datetime.now() - t_start[centre]))
 
-    with ThreadPoolExecutor(max_workers=max(1, writers)) as pool:
-        for i, hh in enumerate(starts):
-            loopStart = datetime.now()
-            centre = hh + NtSlice
-            if verbose:
-                print(str(datetime.now()) + ' - Processing frame ' + str(centre) + '...')
-            for t in range(hh + off, hh + off + kt):
-                if t not in resident:
-                    upload(t)
-            copy_stream.synchronize()
-            ptrs = (C.c_void_p * kt)(*[ring[(hh + off + k) % kt].data_ptr() for k in range(kt)])
-            optr = [C.c_void_p(o.data_ptr()) for o in d_out]
-            if ndim == 2:
-                optr = [optr[0], optr[1], None, optr[2]]
-            rc = lib.of3d_flow_frames(ctx.handle, ndim, ptrs, code, _lib.DEVICE, Nz if ndim == 3 else 1, Ny, Nx, C.byref(taps), prec,
-                                      0, optr[0], optr[1], optr[2], optr[3], _lib.DEVICE)
-            _lib.check(rc, 'of3d_flow_frames')
-            slot = i % 2
-            if pending[slot] is not None:
-                pending[slot].result()                 # the writer that used these host buffers has finished
-            for o, h in zip(d_out, h_out[slot]):
-                torch.from_numpy(h.reshape(-1).view(np.uint8)).copy_(o, non_blocking=True)
-            torch.cuda.current_stream(tdev).synchronize()
-            tstr = str(centre).zfill(4)
-            pending[slot] = pool.submit(write_all, h_out[slot], tstr)
-            if verbose:
-                print(str(datetime.now()) + ' - Frame ' + str(centre) + ' saved.  Duration: ' + str(datetime.now() - loopStart))
-        for p in pending:
-            if p is not None:
-                p.result()
+    # frames needed by this rank: window starts hh in `starts` touch frames hh+off .. hh+off+kt-1
+    t_lo, t_hi = starts[0] + off, starts[-1] + off + kt
+    from collections import deque
+    with ThreadPoolExecutor(max_workers=max(1, min(int(writers), 2))) as pool:
+        futs = deque()                                     # writers in flight; a result stays valid for two more pushes
+        for t in range(t_lo, t_hi):
+            while len(futs) > 1:
+                futs.popleft().result()
+            centre_next = t - (kt - 1) + kt // 2           # centre of the window this frame completes
+            if t - t_lo >= kt - 1:
+                t_start[centre_next] = datetime.now()
+                if verbose:
+                    print(str(datetime.now()) + ' - Processing frame ' + str(centre_next) + '...')
+            done = eng.push(src.frame(t).astype(in_dt, copy=False))
+            if done is not None:
+                futs.append(pool.submit(write_all, done[1], done[0]))
+        done = eng.flush()
+        if done is not None:
+            futs.append(pool.submit(write_all, done[1], done[0]))
+        for f in futs:
+            f.result()
+    eng.close()

@@ -107,3 +107,23 @@ def test_zslab_nccl_two_gpus():
     ref = calc_flow3D(img, *sig, rel_dtype='float64')
     for k in range(4):
         assert np.array_equal(np.concatenate([got[r][k] for r in range(2)], axis=0), ref[k])
+
+
+def test_flowstream_matches_per_window_calls():
+    """The streaming engine (device frame ring, overlapped copies) returns exactly what calc_flow3D returns on each window."""
+    from opticalflow3d_dev_b200.calc_flow import calc_flow3D
+    from opticalflow3d_dev_b200.timelapse import FlowStream
+    img = make_stack((12, 9, 34, 40), seed=41, dtype=np.uint16)
+    eng = FlowStream(img.shape[1:], np.uint16, (1, 1, 2))
+    got = {}
+    for t in range(img.shape[0]):
+        d = eng.push(img[t])
+        if d is not None:
+            got[d[0]] = [a.copy() for a in d[1]]
+    d = eng.flush()
+    got[d[0]] = [a.copy() for a in d[1]]
+    eng.close()
+    assert sorted(got) == [3, 4, 5, 6, 7, 8]
+    for c, arrs in got.items():
+        ref = calc_flow3D(img[c - 3:c + 4], 1, 1, 2, rel_dtype='float64')
+        assert all(np.array_equal(a, r) for a, r in zip(arrs, ref)), c
