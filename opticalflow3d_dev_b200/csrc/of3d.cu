@@ -252,6 +252,19 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
         for (int k = 0; k < t->nT; ++k) if (!frames[k]) { set_error("null frame pointer"); return OF3D_ERR_ARG; }
     }
     if (stage != 0 && (!ic_dev || !dt0_dev)) { set_error("null ic/dt0 pointer"); return OF3D_ERR_ARG; }
+    {
+        // device buffers of the compute type are accessed with 8-byte (fp64) / 4-byte (fp32) vector-free loads and
+        // cp.async: they must be naturally aligned
+        const uintptr_t al = precision == OF3D_FP32 ? 4 : 8;
+        const void* chk[6] = {stage != 0 ? ic_dev : nullptr, stage != 0 ? dt0_dev : nullptr,
+                              out_mem == OF3D_DEVICE ? vx : nullptr, out_mem == OF3D_DEVICE ? vy : nullptr,
+                              out_mem == OF3D_DEVICE ? vz : nullptr, out_mem == OF3D_DEVICE ? rel : nullptr};
+        for (const void* q : chk)
+            if (q && reinterpret_cast<uintptr_t>(q) % al) { set_error("device buffers must be aligned to the compute type"); return OF3D_ERR_ARG; }
+        if (stage != 2 && in_mem == OF3D_DEVICE)
+            for (int k = 0; k < t->nT; ++k)
+                if (reinterpret_cast<uintptr_t>(frames[k]) % dtype_size(in_dtype)) { set_error("frame pointers must be aligned to the image dtype"); return OF3D_ERR_ARG; }
+    }
     if (stage != 1 && (!vx || !vy || !rel || (ndim == 3 && !vz))) { set_error("null image or output pointer"); return OF3D_ERR_ARG; }
     OF3D_CUDA_TRY(cudaSetDevice(c->device));
 

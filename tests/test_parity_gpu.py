@@ -290,3 +290,36 @@ def test_full_size_fast_path_matches_generic_kernels(shape, sig, ndim):
     assert float(fast[-1].min()) > -1e-9 * lam          # smallest eigenvalue of a PSD window tensor
     del fast, gen, win
     torch.cuda.empty_cache()
+
+
+def test_tap_counts_without_specialised_kernels_fall_back_to_generic():
+    """wSig = 9 -> 55 window taps, xyzSig = 5 -> 31 gradient taps: no marching/strip instantiation; the generic
+    kernels must take over transparently and still match the oracle."""
+    from opticalflow3d_dev_b200.synth import make_stack
+    img = make_stack((7, 10, 36, 40), seed=51, dtype=np.uint16)
+    for sig in ((1, 1, 9), (5, 1, 2)):
+        ref = orc.lk_flow3d(img, *sig, rel_mode='float64')
+        out = _cf().calc_flow3D(img, *sig, rel_dtype='float64')
+        assert_flow_close(out[:3], ref[:3], ref[3], 1e-9, str(sig))
+    img2 = make_stack((7, 60, 70), seed=52, dtype=np.uint16)
+    ref = orc.lk_flow2d(img2, 1, 1, 9)
+    out = _cf().calc_flow2D(img2, 1, 1, 9)
+    assert_flow_close(out[:2], ref[:2], ref[2], 1e-9, '2d wSig=9')
+
+
+def test_misaligned_device_buffers_are_rejected():
+    import ctypes as C
+    import torch
+    from opticalflow3d_dev_b200 import _lib
+    from opticalflow3d_dev_b200.taps import flow_taps
+    ctx = _lib.get_context(0)
+    taps, keep = _lib.make_taps(flow_taps(1, 1, 2))
+    raw = torch.zeros(7 * 4 * 8 * 8 * 2 + 16, dtype=torch.uint8, device='cuda')
+    outs = [torch.zeros(4 * 8 * 8 + 1, dtype=torch.float64, device='cuda') for _ in range(4)]
+    torch.cuda.synchronize()
+    rc = ctx.lib.of3d_flow3d(ctx.handle, C.c_void_p(raw.data_ptr() + 1), _lib.U16, _lib.DEVICE, 7, 4, 8, 8, C.byref(taps), _lib.FP64, 0,
+                             *[C.c_void_p(o.data_ptr()) for o in outs], _lib.DEVICE)
+    assert rc == -1 and 'aligned' in _lib.last_error()
+    rc = ctx.lib.of3d_flow3d(ctx.handle, C.c_void_p(raw.data_ptr()), _lib.U16, _lib.DEVICE, 7, 4, 8, 8, C.byref(taps), _lib.FP64, 0,
+                             C.c_void_p(outs[0].data_ptr() + 4), *[C.c_void_p(o.data_ptr()) for o in outs[1:]], _lib.DEVICE)
+    assert rc == -1 and 'aligned' in _lib.last_error()
