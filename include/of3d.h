@@ -160,6 +160,22 @@ OF3D_API int of3d_host_alloc(void** ptr, size_t bytes);
 OF3D_API int of3d_host_free(void* ptr);
 
 /*
+ * Downstream analysis step (reference src/Python/example_analysis_script.ipynb cells 4-6), on device buffers:
+ *   of3d_order_stats  the k_lo-th and k_hi-th smallest elements (0-based ranks among the n values) of a float / double
+ *                     array by radix select: what np.percentile(rel, relPer) interpolates between (cell 4).  *n_nan
+ *                     receives the number of NaNs; when it is non-zero NumPy's answer is NaN and the ranks are not computed.
+ *   of3d_mask_derive  relMask = rel > thresh; v = v * relMask; v[v == 0] = nan; v = v * scale / tscale (xyscale for
+ *                     vx, vy; zscale for vz); Magnitude = sqrt(vx^2+vy^2+vz^2); theta = arctan2(vy, vx);
+ *                     phi = arctan(vz / sqrt(vx^2+vy^2)) (cells 5-6), one fused pass.  vz/oz/phi may be null (2D).
+ *                     Outputs have the dtype of the velocities.
+ */
+OF3D_API int of3d_order_stats(of3d_ctx* ctx, const void* data_dev, int is_f64, int64_t n, int64_t k_lo, int64_t k_hi,
+                              double* out_lo, double* out_hi, int64_t* n_nan);
+OF3D_API int of3d_mask_derive(of3d_ctx* ctx, const void* vx, const void* vy, const void* vz, const void* rel, int v_f64, int rel_f64,
+                              int64_t n, double thresh, double xyscale, double zscale, double tscale,
+                              void* ox, void* oy, void* oz, void* mag, void* theta, void* phi);
+
+/*
  * Benchmark utility: fill a device buffer (nt, nz, ny, nx) of uint16 with the synthetic
  * translating / deforming Gaussian-blob model of SURVEY.md 8(d) (one blob per 16^3 cell,
  * counter-based hashing, offset 100, Gaussian noise sigma 5).  t0 is the time index of the

@@ -8,5 +8,6 @@ Importing the package does not touch the GPU; the first call loads libof3d.so an
 if the library or a CUDA device is missing (there is no CPU fallback).
 """
 from .calc_flow import calc_flow2D, calc_flow3D, process_flow  # noqa: F401
+from .analysis import masked_flow, reliability_threshold  # noqa: F401
 
 __version__ = '0.1.0'

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 import threading
 
@@ -47,6 +48,9 @@ SIGNATURES = {
     'of3d_launch_count': (_i64, [_vp]),
     'of3d_host_alloc': (_i, [C.POINTER(_vp), _sz]),
     'of3d_host_free': (_i, [_vp]),
+    'of3d_order_stats': (_i, [_vp, _vp, _i, _i64, _i64, _i64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
+    'of3d_mask_derive': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
+                              _vp, _vp, _vp, _vp, _vp, _vp]),
     'of3d_synth_blobs': (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, C.c_uint64]),
 }
 
@@ -146,20 +150,8 @@ def pinned_empty(shape, dtype):
     nbytes = int(np.prod(shape)) * dtype.itemsize
     p = C.c_void_p()
     check(lib.of3d_host_alloc(C.byref(p), max(nbytes, 1)), 'of3d_host_alloc')
-    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
-
-        def __del__(self):
-            try:
-                lib.of3d_host_free(self.ptr)
-            except Exception:
-                pass
-    _PINNED[id(buf)] = (buf, _Owner(p))
-    return arr
-
-
-_PINNED = {}
+    # a Python-level subclass of the ctypes array can carry a finalizer: the pinned block is released when the last
+    # NumPy view of it dies (the views keep `buf` alive through their .base chain)
+    buf = type('PinnedBuffer', (C.c_char * max(nbytes, 1),), {}).from_address(p.value)
+    weakref.finalize(buf, lib.of3d_host_free, p).atexit = False      # the driver reclaims it at process exit
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

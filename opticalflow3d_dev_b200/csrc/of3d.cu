@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "kernels_analysis.cuh"
 #include "kernels_generic.cuh"
 #include "kernels_synth.cuh"
 #include "solve.cuh"
@@ -335,6 +336,43 @@ static int flow_contig(of3d_ctx* c, int ndim, const void* images, int in_dtype, 
     return flow_frames_impl(c, ndim, frames, in_dtype, in_mem, nz, ny, nx, t, precision, flags, vx, vy, vz, rel, out_mem);
 }
 
+
+// k-th smallest (0-based) non-NaN element by MSB-first radix select; *n_nan = number of NaNs in the array
+template <typename Tv, typename Key>
+static int order_stat(of3d_ctx* c, const Tv* x, int64_t n, int64_t k, double* out, int64_t* n_nan) {
+    constexpr int KEYBITS = sizeof(Key) * 8;
+    unsigned long long* d = ws_take<unsigned long long>(c, kRadixBins + 1);
+    std::vector<unsigned long long> h(kRadixBins + 1);
+    Key prefix = 0, mask = 0;
+    int shift = KEYBITS;
+    while (shift > 0) {
+        const int bits = std::min(kRadixBits, shift);
+        shift -= bits;
+        OF3D_CUDA_TRY(cudaMemsetAsync(d, 0, (kRadixBins + 1) * sizeof(unsigned long long), c->stream));
+        radix_hist<Tv, Key><<<grid_for(c, n), 256, 0, c->stream>>>(x, n, prefix, mask, shift, (1u << bits) - 1u, d, d + kRadixBins);
+        c->launches++;
+        OF3D_CUDA_TRY(cudaMemcpyAsync(h.data(), d, (kRadixBins + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (n_nan) *n_nan = (int64_t)h[kRadixBins];
+        const int nb = 1 << bits;
+        int b = 0;
+        for (; b < nb; ++b) {
+            if ((unsigned long long)k < h[b]) break;
+            k -= (int64_t)h[b];
+        }
+        if (b == nb) { set_error("rank beyond the number of non-NaN elements"); return OF3D_ERR_ARG; }
+        prefix |= (Key)b << shift;
+        mask |= (Key)(nb - 1) << shift;
+    }
+    // invert sort_key
+    const Key top = (Key)1 << (KEYBITS - 1);
+    const Key bits = (prefix & top) ? (prefix & ~top) : ~prefix;
+    Tv v;
+    memcpy(&v, &bits, sizeof(v));
+    *out = (double)v;
+    return OF3D_OK;
+}
+
 }  // namespace of3d
 
 // =============================================================================================
@@ -448,6 +486,43 @@ OF3D_API int of3d_host_alloc(void** ptr, size_t bytes) {
 
 OF3D_API int of3d_host_free(void* ptr) {
     if (ptr) cudaFreeHost(ptr);
+    return OF3D_OK;
+}
+
+OF3D_API int of3d_order_stats(of3d_ctx* c, const void* data_dev, int is_f64, int64_t n, int64_t k_lo, int64_t k_hi, double* out_lo,
+                              double* out_hi, int64_t* n_nan) {
+    if (!c || !data_dev || n < 1 || k_lo < 0 || k_hi < k_lo || k_hi >= n || !out_lo || !out_hi) { set_error("bad argument"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    if (int rc = ws_ensure(c, 1 << 20)) return rc;
+    c->ws_off = 0;
+    int64_t nn = 0;
+    int rc = is_f64 ? order_stat<double, uint64_t>(c, (const double*)data_dev, n, k_lo, out_lo, &nn)
+                    : order_stat<float, uint32_t>(c, (const float*)data_dev, n, k_lo, out_lo, &nn);
+    if (n_nan) *n_nan = nn;
+    if (rc || nn > 0) { if (nn > 0) *out_hi = *out_lo; return rc; }      // NaNs present: the caller returns NaN like NumPy
+    if (k_hi == k_lo) { *out_hi = *out_lo; return OF3D_OK; }
+    return is_f64 ? order_stat<double, uint64_t>(c, (const double*)data_dev, n, k_hi, out_hi, nullptr)
+                  : order_stat<float, uint32_t>(c, (const float*)data_dev, n, k_hi, out_hi, nullptr);
+}
+
+OF3D_API int of3d_mask_derive(of3d_ctx* c, const void* vx, const void* vy, const void* vz, const void* rel, int v_f64, int rel_f64,
+                              int64_t n, double thresh, double xyscale, double zscale, double tscale, void* ox, void* oy, void* oz,
+                              void* mag, void* theta, void* phi) {
+    if (!c || !vx || !vy || !rel || !ox || !oy || !mag || !theta || n < 1 || (vz && (!oz || !phi))) { set_error("bad argument"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    const int grid = grid_for(c, n);
+#define OF3D_MD(TV, TR)                                                                                                        \
+    mask_derive<TV, TR><<<grid, 256, 0, c->stream>>>((const TV*)vx, (const TV*)vy, (const TV*)vz, (const TR*)rel, n, (TR)thresh,  \
+                                                    (TV)xyscale, (TV)zscale, (TV)tscale, (TV*)ox, (TV*)oy, (TV*)oz, (TV*)mag,    \
+                                                    (TV*)theta, (TV*)phi)
+    if (v_f64 && rel_f64) OF3D_MD(double, double);
+    else if (v_f64) OF3D_MD(double, float);
+    else if (rel_f64) OF3D_MD(float, double);
+    else OF3D_MD(float, float);
+#undef OF3D_MD
+    c->launches++;
+    OF3D_CUDA_TRY(cudaGetLastError());
+    OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return OF3D_OK;
 }
 

@@ -127,3 +127,23 @@ def test_flowstream_matches_per_window_calls():
     for c, arrs in got.items():
         ref = calc_flow3D(img[c - 3:c + 4], 1, 1, 2, rel_dtype='float64')
         assert all(np.array_equal(a, r) for a, r in zip(arrs, ref)), c
+
+
+def test_pinned_buffers_are_released():
+    """pinned_empty blocks are freed when the last NumPy view dies (they used to be kept for the process lifetime)"""
+    import gc
+    import weakref
+    from opticalflow3d_dev_b200 import _lib
+    a = _lib.pinned_empty((4, 1024), np.float32)
+    a[:] = 3.0
+    row = a[1]
+    base = a
+    while getattr(base, 'base', None) is not None:
+        base = base.base
+    ref = weakref.ref(base)
+    del a, base
+    gc.collect()
+    assert ref() is not None and row[5] == 3.0        # a view keeps the block
+    del row
+    gc.collect()
+    assert ref() is None
