@@ -92,6 +92,41 @@ def alg_fma_per_voxel(sig, ndim):
     return (kt - 1) + 2 * kr + 2 * kr + 2 * ks + 5 + 10 * kw + 30
 
 
+def stage_model(sig, ndim, precision, in_itemsize=2):
+    """Per-stage algorithmic bytes and FMAs per voxel of the marching pipeline: every stage reads its
+    inputs once and writes its outputs once; FMA counts are those of the direct separable evaluation the stage performs."""
+    e = 8 if precision == 'fp64' else 4
+    kr = 2 * math.ceil(3 * sig[0]) + 1
+    ks = 2 * math.ceil(3 * sig[0] / 4) + 1
+    kt = 2 * math.ceil(3 * sig[1]) + 1
+    kw = 2 * math.ceil(3 * sig[2]) + 1
+    if ndim == 3:
+        return {'temporal': (kt * in_itemsize + 2 * e, kt - 1),
+                'gradient_xy': (2 * e + 4 * e, 4 * kr + 3 * ks),
+                'gradient_z': (4 * e + 4 * e, 2 * kr + 2 * ks),
+                'products_window_z': (4 * e + 9 * e, 9 + 9 * kw),
+                'window_xy_solve': (9 * e + 4 * e, 18 * kw + 120)}
+    return {'temporal': (kt * in_itemsize + 2 * e, kt - 1),
+            'gradient_xy': (2 * e + 3 * e, 4 * kr + 2 * ks),
+            'window_xy_solve': (3 * e + 3 * e, 5 + 10 * kw + 30)}
+
+
+def stage_report(stages, model, vol, timepoints, hbm_peak, fma_pk):
+    """stages = Context.stage_times() of `timepoints` operator calls -> per-stage roofline rows, longest first"""
+    rows = []
+    for name, (ms, n) in stages.items():
+        per_tp = ms / max(timepoints, 1)
+        row = {'stage': name, 'ms_per_timepoint': per_tp, 'launches_per_timepoint': n / max(timepoints, 1)}
+        if name in model and per_tp > 0:
+            b, f = model[name]
+            row.update({'alg_bytes_per_voxel': b, 'alg_gbs': b * vol / per_tp / 1e6, 'hbm_frac': b * vol / per_tp / 1e6 / hbm_peak,
+                        'alg_fma_per_voxel': f, 'tfma_per_s': f * vol / per_tp / 1e9,
+                        'fp_frac': (f * vol / per_tp / 1e9 / fma_pk) if fma_pk else None})
+        rows.append(row)
+    rows.sort(key=lambda r: -r['ms_per_timepoint'])
+    return rows
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -363,6 +398,8 @@ def gpu_arm(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count()
+    ctx.stage_times()                                            # clear the per-stage accumulators
+    ctx.set_profile(not args.no_stage_events)                    # event brackets around every launch, on the library stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -371,6 +408,8 @@ def gpu_arm(args, rank, world, local_rank):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
+    stages = ctx.stage_times()
+    ctx.set_profile(False)
     clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     lsum = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
@@ -443,6 +482,31 @@ def gpu_arm(args, rank, world, local_rank):
     fma = alg_fma_per_voxel(sig, ndim)
     fpk = fma_peak(args.precision)
     tr = measured_traffic(args.workload, args.precision)
+    # roofline of the DOMINANT kernel, timed live by the library's event brackets on its own stream during the timed
+    # region (rank 0); the whole-pipeline figures (window read once, outputs written once) ride along
+    pipeline = {'alg_bytes_per_voxel': bpv, 'alg_gbs': ach, 'hbm_frac': ach / peak,
+                'traffic_bytes_per_voxel': (tr['bytes_per_voxel'] if tr else None),
+                'alg_fma_per_voxel': fma, 'tfma_per_s': value * fma / 1e12 / world,
+                'fp_frac': (value * fma / 1e12 / world / fpk) if fpk else None,
+                'launch': 'one output timepoint = %s kernels' % (tr['kernels'] if tr else 'several')}
+    rows = stage_report(stages, stage_model(sig, ndim, args.precision), vol, len(mine) * args.steps, peak, fpk)
+    top = next((r for r in rows if 'alg_gbs' in r), None)
+    if top:
+        full = args.shape is None and args.timepoints is None and not args.generic
+        sd = (tr or {}).get('stage_dram_bytes_per_launch', {}) if full else {}
+        roof = {'bound': 'hbm', 'kernel': top['stage'], 'achieved': top['alg_gbs'], 'peak': peak, 'unit': 'GB/s',
+                'frac': top['hbm_frac'], 'traffic': sd.get(top['stage']), 'peak_source': peak_src,
+                'alg_bytes_per_voxel': top['alg_bytes_per_voxel'], 'alg_bytes_per_launch': top['alg_bytes_per_voxel'] * vol,
+                'launch_ms': top['ms_per_timepoint'], 'share_of_step': top['ms_per_timepoint'] * len(mine) * args.steps / ms,
+                'fp_pipe': {'alg_fma_per_voxel': top['alg_fma_per_voxel'], 'achieved_tfma_per_s': top['tfma_per_s'],
+                            'peak_tfma_per_s': fpk, 'frac': top['fp_frac'],
+                            'note': 'the roof that binds this kernel is the CUDA-core FMA pipe (measured peak, '
+                                    'tools/fma_peak.cu), not HBM; see DESIGN.md 3.3'},
+                'stages': rows, 'pipeline': pipeline}
+    else:                                                        # generic kernels / stage events disabled
+        roof = {'bound': 'hbm', 'kernel': 'whole pipeline', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                'traffic': (tr['bytes_per_voxel'] * vol if tr else None), 'peak_source': peak_src,
+                'alg_bytes_per_voxel': bpv, 'alg_bytes_per_launch': bpv * vol, 'stages': rows, 'pipeline': pipeline}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
@@ -451,14 +515,7 @@ def gpu_arm(args, rank, world, local_rank):
                    'output_timepoints_per_step': len(outs_all), 'sharding': 'output timepoint, no collective',
                    'l2': 'inputs+intermediates per timepoint (>= %.1f GB) exceed the 126 MB L2' % (kt * vol * 2 / 1e9),
                    'kernels': 'generic' if args.generic else 'default'},
-        'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                     'traffic': (tr['bytes_per_voxel'] * vol if tr else None),
-                     'peak_source': peak_src, 'alg_bytes_per_voxel': bpv,
-                     'alg_bytes_per_launch': bpv * vol, 'launch': 'one output timepoint = the whole pipeline (%s kernels)' %
-                     (tr['kernels'] if tr else 'several'), 'traffic_bytes_per_voxel': (tr['bytes_per_voxel'] if tr else None),
-                     'fp_pipe': {'alg_fma_per_voxel': fma, 'achieved_tfma_per_s': value * fma / 1e12 / world,
-                                 'peak_tfma_per_s': fpk, 'frac': value * fma / 1e12 / world / fpk,
-                                 'note': 'the binding roof is the CUDA-core FMA pipe (measured peak, tools/fma_peak.cu); see DESIGN.md'}},
+        'roofline': roof,
         'clocks': clocks, 'gpu_launches': int(lsum.item()), 'e2e': e2e,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -486,6 +543,7 @@ def main():
     ap.add_argument('--generic', action='store_true', help='force the generic kernels')
     ap.add_argument('--e2e-timepoints', type=int, default=6)
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-stage-events', action='store_true', help='do not bracket the launches with CUDA events')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-voxels', type=int, default=400_000, help='voxels per core per CPU step')
     ap.add_argument('--cpu-cores', type=int, default=None)

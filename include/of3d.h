@@ -155,6 +155,23 @@ OF3D_API int of3d_sync(of3d_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 OF3D_API int64_t of3d_launch_count(of3d_ctx* ctx);
 
+/*
+ * Per-stage device time (measurement hook, nothing in the reference): with profiling on, every kernel launch of the
+ * flow operators is bracketed by two CUDA events on the context's stream.  of3d_stage_times synchronises, adds the
+ * elapsed time (ms) and launch count of every bracket since the last call into ms[OF3D_N_STAGES] /
+ * launches[OF3D_N_STAGES] (either may be null) and clears the accumulators.
+ */
+#define OF3D_STAGE_TEMPORAL 0         /* calc_flow.py:276-278  temporal derivative of the centre frame          */
+#define OF3D_STAGE_GRAD_XY 1          /* calc_flow.py:279-312  in-plane passes of dx, dy, dz, dt                */
+#define OF3D_STAGE_GRAD_Z 2           /* calc_flow.py:279-312  z passes of dx, dy, dz, dt                       */
+#define OF3D_STAGE_WINDOW_Z 3         /* calc_flow.py:315-331  nine products and the z pass of the window       */
+#define OF3D_STAGE_WINDOW_XY_SOLVE 4  /* calc_flow.py:315-357  in-plane window passes, solve, reliability       */
+#define OF3D_STAGE_GENERIC 5          /* the same lines on the generic (any tap count / bit-exact) kernels      */
+#define OF3D_N_STAGES 6
+OF3D_API int of3d_set_profile(of3d_ctx* ctx, int enable);
+OF3D_API int of3d_stage_times(of3d_ctx* ctx, double* ms, int64_t* launches);
+OF3D_API const char* of3d_stage_name(int stage);
+
 /* Pinned host buffers for callers that want full-rate host<->device copies. */
 OF3D_API int of3d_host_alloc(void** ptr, size_t bytes);
 OF3D_API int of3d_host_free(void* ptr);

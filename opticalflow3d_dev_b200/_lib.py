@@ -48,6 +48,9 @@ SIGNATURES = {
     'of3d_launch_count': (_i64, [_vp]),
     'of3d_host_alloc': (_i, [C.POINTER(_vp), _sz]),
     'of3d_host_free': (_i, [_vp]),
+    'of3d_set_profile': (_i, [_vp, _i]),
+    'of3d_stage_times': (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
+    'of3d_stage_name': (C.c_char_p, [_i]),
     'of3d_order_stats': (_i, [_vp, _vp, _i, _i64, _i64, _i64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
     'of3d_mask_derive': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
                               _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -128,6 +131,16 @@ class Context:
 
     def set_async(self, on):
         check(self.lib.of3d_set_async(self.handle, int(bool(on))), 'of3d_set_async')
+
+    def set_profile(self, on):
+        check(self.lib.of3d_set_profile(self.handle, int(bool(on))), 'of3d_set_profile')
+
+    def stage_times(self):
+        """{stage name: (device ms, launches)} since the last call (synchronises the library stream)"""
+        n = 6                                                   # OF3D_N_STAGES
+        ms, cnt = (C.c_double * n)(), (_i64 * n)()
+        check(self.lib.of3d_stage_times(self.handle, ms, cnt), 'of3d_stage_times')
+        return {self.lib.of3d_stage_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}
 
 
 _tls = threading.local()

@@ -1,5 +1,6 @@
 // Shared declarations for libof3d (sm_100a). Internal header.
 #pragma once
+#include <vector>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -59,9 +60,35 @@ struct of3d_ctx {
     int async = 0;
     int64_t launches = 0;
     int sm_count = 148;
+    // optional per-stage device timing (of3d_set_profile): every launch is bracketed by events on `stream`
+    int profile = 0;
+    std::vector<cudaEvent_t> ev_pool;                 // recycled events
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> spans;                          // recorded, not yet resolved
+    double stage_ms[OF3D_N_STAGES] = {};
+    int64_t stage_launches[OF3D_N_STAGES] = {};
 };
 
 namespace of3d {
+
+// Brackets the launches issued during its lifetime with two events when the context is profiling.
+struct StageScope {
+    of3d_ctx* c;
+    int stage;
+    cudaEvent_t a = nullptr;
+    static cudaEvent_t take(of3d_ctx* c) {
+        cudaEvent_t e = nullptr;
+        if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    StageScope(of3d_ctx* ctx, int st) : c(ctx), stage(st) {
+        if (c->profile) { a = take(c); cudaEventRecord(a, c->stream); }
+    }
+    ~StageScope() {
+        if (a) { cudaEvent_t b = take(c); cudaEventRecord(b, c->stream); c->spans.push_back({stage, a, b}); }
+    }
+};
 
 template <typename P>
 static inline P* ws_take(of3d_ctx* c, size_t count) {

@@ -102,6 +102,7 @@ struct GenericPipe {
         const int64_t n = s.n();
         const int64_t len = axis == 0 ? s.nz : (axis == 1 ? s.ny : s.nx);
         const int64_t stride = axis == 0 ? s.ny * s.nx : (axis == 1 ? s.nx : 1);
+        StageScope span(c, OF3D_STAGE_GENERIC);
         corr_axis_generic<T, EXACT><<<grid_for(c, n), 256, 0, c->stream>>>(in, out, n, len, stride, f);
         c->launches++;
     }
@@ -114,6 +115,7 @@ struct GenericPipe {
 
     template <typename Tin>
     void temporal(const FramePtrs& fp, T* ic, T* dt0) {
+        StageScope span(c, OF3D_STAGE_TEMPORAL);
         const int64_t n = s.n();
         if (!EXACT) {
             // 16-byte vector path when every frame (and the outputs) is 16-byte aligned; scalar kernel for the tail
@@ -180,10 +182,12 @@ struct GenericPipe {
             for (int i = 0; i < 5; ++i) { pa[i] = A[i]; pb[i] = B[i]; }
         }
         for (int ch = 0; ch < nch; ++ch) {
+            StageScope span(c, OF3D_STAGE_GENERIC);
             product_generic<T><<<grid_for(c, n), 256, 0, c->stream>>>(pa[ch], pb[ch], prod, n);
             c->launches++;
             chain(prod, w + (size_t)ch * n, t1, t2, fW, fW, fW);  // :300-313 / 133-141
         }
+        StageScope span(c, OF3D_STAGE_GENERIC);
         if (s.ndim == 3) solve3_generic<T, EXACT><<<grid_for(c, n), 256, 0, c->stream>>>(w, n, vx, vy, vz, rel);
         else solve2_generic<T, EXACT><<<grid_for(c, n), 256, 0, c->stream>>>(w, n, vx, vy, rel);
         c->launches++;
@@ -414,6 +418,8 @@ OF3D_API int of3d_destroy(of3d_ctx* c) {
     if (!c) return OF3D_OK;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->ws) cudaFree(c->ws);
     delete c;
     return OF3D_OK;
@@ -476,6 +482,39 @@ OF3D_API int of3d_sync(of3d_ctx* c) {
 }
 
 OF3D_API int64_t of3d_launch_count(of3d_ctx* c) { return c ? c->launches : 0; }
+
+OF3D_API int of3d_set_profile(of3d_ctx* c, int enable) {
+    if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
+    c->profile = enable ? 1 : 0;
+    return OF3D_OK;
+}
+
+OF3D_API int of3d_stage_times(of3d_ctx* c, double* ms, int64_t* launches) {
+    if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (const auto& sp : c->spans) {
+        float t = 0.f;
+        OF3D_CUDA_TRY(cudaEventElapsedTime(&t, sp.a, sp.b));
+        c->stage_ms[sp.stage] += t;
+        c->stage_launches[sp.stage]++;
+        c->ev_pool.push_back(sp.a);
+        c->ev_pool.push_back(sp.b);
+    }
+    c->spans.clear();
+    for (int i = 0; i < OF3D_N_STAGES; ++i) {
+        if (ms) ms[i] = c->stage_ms[i];
+        if (launches) launches[i] = c->stage_launches[i];
+        c->stage_ms[i] = 0.0;
+        c->stage_launches[i] = 0;
+    }
+    return OF3D_OK;
+}
+
+OF3D_API const char* of3d_stage_name(int stage) {
+    static const char* names[OF3D_N_STAGES] = {"temporal", "gradient_xy", "gradient_z", "products_window_z", "window_xy_solve", "generic"};
+    return (stage >= 0 && stage < OF3D_N_STAGES) ? names[stage] : "";
+}
 
 OF3D_API int of3d_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) { set_error("ptr is null"); return OF3D_ERR_ARG; }

@@ -147,3 +147,26 @@ def test_pinned_buffers_are_released():
     del row
     gc.collect()
     assert ref() is None
+
+
+def test_stage_times_cover_every_launch():
+    """of3d_set_profile / of3d_stage_times: every launch of one operator call lands in exactly one stage bracket"""
+    from opticalflow3d_dev_b200 import _lib, calc_flow3D
+    ctx = _lib.get_context(0)
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 4000, (7, 40, 96, 128)).astype(np.uint16)
+    calc_flow3D(img, 3, 1, 4)                                   # warm
+    ctx.stage_times()
+    ctx.set_profile(True)
+    try:
+        l0 = ctx.launch_count()
+        calc_flow3D(img, 3, 1, 4)
+        st = ctx.stage_times()
+        assert sum(n for _, n in st.values()) == ctx.launch_count() - l0
+        assert set(st) == {'temporal', 'gradient_xy', 'gradient_z', 'products_window_z', 'window_xy_solve'}
+        assert all(ms > 0 for ms, _ in st.values())
+        assert ctx.stage_times() == {}                           # cleared
+        calc_flow3D(img, 3, 1, 4, generic=True)
+        assert set(ctx.stage_times()) == {'temporal', 'generic'}
+    finally:
+        ctx.set_profile(False)
