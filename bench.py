@@ -454,7 +454,7 @@ def gpu_arm(args, rank, world, local_rank):
             eng.close()
             del eng
             # the synchronous per-window call, for comparison
-            hout = tuple(_lib.pinned_empty(tuple(sp), np_odt) for _ in range(ndim + 1))
+            hout = tuple(_lib.pinned_empty(tuple(sp), np.float32 if (ndim == 3 and i == 3) else np_odt) for i in range(ndim + 1))
             fn = calc_flow3D if ndim == 3 else calc_flow2D
             kw = dict(precision=args.precision, device=local_rank, out=hout, generic=args.generic)
             fn(hfr[0:kt], *sig, **kw)

@@ -65,6 +65,8 @@ extern "C" {
 #define OF3D_FLAG_EXACT 1u    /* generic kernels, scipy's paired summation order, no FMA contraction:
                                  fp64 flow fields bit-identical to the reference */
 #define OF3D_FLAG_GENERIC 2u  /* force the generic (any tap count) kernels, normal rounding */
+#define OF3D_FLAG_REL_F32 4u  /* with OF3D_FP64: `rel` is a float32 buffer, the dtype the reference returns in 3D
+                                 (calc_flow.py:355-357); computed in float64, rounded once on the device */
 
 /*
  * The five sampled, un-normalised 1-D filters of the reference, as float64, each of odd length:

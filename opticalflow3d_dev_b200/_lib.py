@@ -15,7 +15,7 @@ OK = 0
 U8, U16, I16, F32, F64, I32, U32 = range(7)
 FP64, FP32 = 0, 1
 HOST, DEVICE = 0, 1
-FLAG_EXACT, FLAG_GENERIC = 1, 2
+FLAG_EXACT, FLAG_GENERIC, FLAG_REL_F32 = 1, 2, 4
 
 DTYPE_CODES = {np.dtype(np.uint8): U8, np.dtype(np.uint16): U16, np.dtype(np.int16): I16,
                np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32,

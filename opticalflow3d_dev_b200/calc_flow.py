@@ -71,7 +71,7 @@ def _as_supported_host_array(images):
     return np.ascontiguousarray(a)
 
 
-def _run(images, spatialSig, tSig, wSig, ndim, precision, device, exact, generic, out=None):
+def _run(images, spatialSig, tSig, wSig, ndim, precision, device, exact, generic, out=None, rel_f32=False):
     if precision not in ('fp64', 'fp32'):
         raise ValueError("precision must be 'fp64' or 'fp32'")
     if not (spatialSig > 0 and tSig > 0 and wSig > 0):
@@ -80,6 +80,11 @@ def _run(images, spatialSig, tSig, wSig, ndim, precision, device, exact, generic
     taps, keep = _lib.make_taps(tp)
     prec = _lib.FP64 if precision == 'fp64' else _lib.FP32
     flags = (_lib.FLAG_EXACT if exact else 0) | (_lib.FLAG_GENERIC if generic else 0)
+    if out is not None and precision == 'fp64':
+        rel_f32 = getattr(out[-1], 'dtype', None) == np.float32      # the caller's buffer decides
+    rel_f32 = bool(rel_f32) and precision == 'fp64'
+    if rel_f32:
+        flags |= _lib.FLAG_REL_F32                                   # float64 value, rounded once on the device
     nout = ndim + 1
     sp = tuple(int(s) for s in images.shape[1:])
     nt = int(images.shape[0])
@@ -95,19 +100,23 @@ def _run(images, spatialSig, tSig, wSig, ndim, precision, device, exact, generic
         odt = torch.float64 if precision == 'fp64' else torch.float32
         torch.cuda.current_stream(dev).synchronize()       # the library runs on its own stream
         outs = [torch.empty(sp, dtype=odt, device=t.device) for _ in range(nout)]
+        if rel_f32:
+            outs[-1] = torch.empty(sp, dtype=torch.float32, device=t.device)
         ptrs = [C.c_void_p(o.data_ptr()) for o in outs]
         in_ptr, code, mem = C.c_void_p(t.data_ptr()), _lib.DTYPE_CODES[np_dt], _lib.DEVICE
     else:
         a = _as_supported_host_array(images)
         ctx = _lib.get_context(_default_device() if device is None else device)
         odt = np.float64 if precision == 'fp64' else np.float32
+        odts = [odt] * (nout - 1) + [np.float32 if rel_f32 else odt]
         if out is None:
-            outs = [np.empty(sp, dtype=odt) for _ in range(nout)]
+            outs = [np.empty(sp, dtype=d) for d in odts]
         else:
             outs = list(out)
-            if len(outs) != nout or any(not isinstance(o, np.ndarray) or o.shape != sp or o.dtype != odt
-                                        or not o.flags.c_contiguous for o in outs):
-                raise ValueError('out must be %d C-contiguous %s arrays of shape %s' % (nout, np.dtype(odt).name, sp))
+            if len(outs) != nout or any(not isinstance(o, np.ndarray) or o.shape != sp or o.dtype != d
+                                        or not o.flags.c_contiguous for o, d in zip(outs, odts)):
+                raise ValueError('out must be %d C-contiguous %s arrays of shape %s (the reliability may be float32)'
+                                 % (nout, np.dtype(odt).name, sp))
         ptrs = [C.c_void_p(o.ctypes.data) for o in outs]
         in_ptr, code, mem = C.c_void_p(a.ctypes.data), _lib.DTYPE_CODES[a.dtype], _lib.HOST
 
@@ -158,16 +167,16 @@ def calc_flow3D(images, xyzSig=3, tSig=1, wSig=4, *, precision='fp64', device=No
 
     rel_dtype='reference' (default) returns the reliability as float32, the dtype the reference
     returns because it runs the eigen-solver on complex64 (calc_flow.py:355-357); the value is
-    computed in float64 and rounded once.  rel_dtype='float64' keeps the float64 value (what the
+    computed in float64 and rounded once, on the device (OF3D_FLAG_REL_F32), so only 4 bytes per voxel
+    cross PCIe.  With out=, the dtype of out[3] (float32 or float64) decides instead.  rel_dtype='float64' keeps the float64 value (what the
     MATLAB twin's pageeig on doubles gives, calc_flow3D.m:235-236).  Other keyword-only extras as
     in calc_flow2D.
     """
     _validate(images, tSig, 4, _MSG_NDIM_3D)
     if rel_dtype not in ('reference', 'float64'):
         raise ValueError("rel_dtype must be 'reference' or 'float64'")
-    vx, vy, vz, rel = _run(images, xyzSig, tSig, wSig, 3, precision, device, exact, generic, out)
-    if rel_dtype == 'reference' and precision == 'fp64' and out is None:
-        rel = rel.float() if _is_cuda_tensor(rel) else rel.astype(np.float32)
+    vx, vy, vz, rel = _run(images, xyzSig, tSig, wSig, 3, precision, device, exact, generic, out,
+                           rel_f32=(rel_dtype == 'reference'))
     return vx, vy, vz, rel
 
 

@@ -87,6 +87,7 @@ static size_t plan_bytes(int ndim, int64_t kt, int64_t n, int in_dtype, int prec
     b += (size_t)std::max(generic_volumes(ndim), 2 + fast_volumes(ndim)) * align_up((size_t)n * ts);
     if (in_mem == OF3D_HOST) b += (size_t)kt * align_up((size_t)n * dtype_size(in_dtype));
     if (out_mem == OF3D_HOST) b += (size_t)(ndim + 1) * align_up((size_t)n * ts);
+    if (precision == OF3D_FP64) b += align_up((size_t)n * 8);     // float64 reliability scratch of OF3D_FLAG_REL_F32
     return b + 4096;
 }
 
@@ -264,6 +265,8 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
         const void* chk[6] = {stage != 0 ? ic_dev : nullptr, stage != 0 ? dt0_dev : nullptr,
                               out_mem == OF3D_DEVICE ? vx : nullptr, out_mem == OF3D_DEVICE ? vy : nullptr,
                               out_mem == OF3D_DEVICE ? vz : nullptr, out_mem == OF3D_DEVICE ? rel : nullptr};
+        if ((flags & OF3D_FLAG_REL_F32) && reinterpret_cast<uintptr_t>(rel) % 4) { set_error("device buffers must be aligned to the compute type"); return OF3D_ERR_ARG; }
+        if (flags & OF3D_FLAG_REL_F32) chk[5] = nullptr;
         for (const void* q : chk)
             if (q && reinterpret_cast<uintptr_t>(q) % al) { set_error("device buffers must be aligned to the compute type"); return OF3D_ERR_ARG; }
         if (stage != 2 && in_mem == OF3D_DEVICE)
@@ -301,6 +304,10 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
     const int* oidx = ndim == 3 ? oidx3 : oidx2;
     if (stage != 1 && out_mem == OF3D_HOST)
         for (int i = 0; i < nout; ++i) dout[oidx[i]] = ws_take<char>(c, (size_t)n * ts);
+    // OF3D_FLAG_REL_F32: the kernels write the float64 reliability to scratch; one narrowing pass fills the float32 buffer
+    const bool narrow = stage != 1 && precision == OF3D_FP64 && (flags & OF3D_FLAG_REL_F32);
+    void* rel_f32 = dout[3];
+    if (narrow) dout[3] = ws_take<char>(c, (size_t)n * 8);
 
     const FramePtrs* fpp = stage == 2 ? nullptr : &fp;
     int rc;
@@ -311,10 +318,17 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
         rc = run_typed<float>(c, s, fpp, in_dtype, t, flags, ic_dev, dt0_dev, stage == 1 ? ic_dev : nullptr,
                               stage == 1 ? dt0_dev : nullptr, stage != 1, dout);
     if (rc) return rc;
+    if (narrow) {
+        StageScope span(c, OF3D_STAGE_WINDOW_XY_SOLVE);           // epilogue of calc_flow.py:355-357
+        narrow_f64_f32<<<grid_for(c, n), 256, 0, c->stream>>>((const double*)dout[3], (float*)rel_f32, n);
+        c->launches++;
+        dout[3] = rel_f32;
+    }
     OF3D_CUDA_TRY(cudaGetLastError());
     if (stage != 1 && out_mem == OF3D_HOST)
         for (int i = 0; i < nout; ++i)
-            OF3D_CUDA_TRY(cudaMemcpyAsync(out[oidx[i]], dout[oidx[i]], (size_t)n * ts, cudaMemcpyDeviceToHost, c->stream));
+            OF3D_CUDA_TRY(cudaMemcpyAsync(out[oidx[i]], dout[oidx[i]], (size_t)n * ((narrow && oidx[i] == 3) ? 4 : ts),
+                                          cudaMemcpyDeviceToHost, c->stream));
     const bool all_device = (stage == 2 || in_mem == OF3D_DEVICE) && (stage == 1 || out_mem == OF3D_DEVICE);
     if (!(c->async && all_device)) OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return OF3D_OK;

@@ -160,7 +160,7 @@ class FlowStream:
       two device output sets, and the device->host copy of that set runs on a second copy stream while the NEXT
       window computes;
     * results are returned one call later as views of pinned host buffers; three host buffer sets rotate, so a
-      returned result stays valid during the next TWO calls of push() -- copy it or finish writing it before the third.
+      returned result stays valid during the NEXT call of push() -- copy it or finish writing it before the one after.
     """
 
     def __init__(self, spatial_shape, dtype, sigmas, precision='fp64', device=None):
@@ -189,9 +189,11 @@ class FlowStream:
         self.ring = torch.empty((self.kt, fbytes), dtype=torch.uint8, device=tdev)       # frame t lives in slot t % kt
         self.stage = [_lib.pinned_empty(self.sp, self.in_dt) for _ in range(2)]
         self.stage_ev = [None, None]
-        self.d_out = [[torch.empty(self.nvox * self.odt.itemsize, dtype=torch.uint8, device=tdev) for _ in range(self.nout)]
-                      for _ in range(2)]
-        self.h_out = [[_lib.pinned_empty(self.sp, self.odt) for _ in range(self.nout)] for _ in range(3)]
+        # 3D reliability leaves the device as float32, the dtype the reference returns (calc_flow.py:355-357)
+        self.flags = _lib.FLAG_REL_F32 if (self.ndim == 3 and precision == 'fp64') else 0
+        self.odts = [self.odt] * (self.nout - 1) + [np.dtype(np.float32) if self.flags else self.odt]
+        self.d_out = [[torch.empty(self.nvox * d.itemsize, dtype=torch.uint8, device=tdev) for d in self.odts] for _ in range(2)]
+        self.h_out = [[_lib.pinned_empty(self.sp, d) for d in self.odts] for _ in range(3)]
         self.s_in = torch.cuda.Stream(device=tdev)
         self.s_out = torch.cuda.Stream(device=tdev)
         self.s_lib = torch.cuda.ExternalStream(self.ctx.stream, device=tdev)
@@ -238,8 +240,9 @@ class FlowStream:
         self.t += 1
         if self.t < self.kt:
             return None
-        # ---- a window is complete: frames t-kt .. t-1, centre t-1-kt//2
-        done = self._collect()                             # result of the previous window (its D2H overlapped our upload)
+        # ---- a window is complete: frames t-kt .. t-1, centre t-1-kt//2.  Its compute and its D2H are enqueued BEFORE
+        # the previous result is waited for, so the output copy stream never idles: D2H(t-1) overlaps compute(t).
+        prev, self.pending = self.pending, None
         slot = self.nwin % 2                               # device output set
         hslot = self.nwin % 3                              # host output set
         first = self.t - self.kt
@@ -252,7 +255,7 @@ class FlowStream:
             o = [o[0], o[1], None, o[2]]
         nz = self.sp[0] if self.ndim == 3 else 1
         rc = self.ctx.lib.of3d_flow_frames(self.ctx.handle, self.ndim, ptrs, self.code, _lib.DEVICE, nz, self.sp[-2], self.sp[-1],
-                                           C.byref(self.taps), self.prec, 0, o[0], o[1], o[2], o[3], _lib.DEVICE)
+                                           C.byref(self.taps), self.prec, self.flags, o[0], o[1], o[2], o[3], _lib.DEVICE)
         _lib.check(rc, 'of3d_flow_frames')
         cev = torch.cuda.Event(); cev.record(self.s_lib)
         self.ring_free_ev = cev
@@ -265,7 +268,10 @@ class FlowStream:
         self.slot_free_ev[slot] = dev_
         self.pending = (first + self.kt // 2, hslot, dev_)
         self.nwin += 1
-        return done
+        if prev is None:
+            return None
+        prev[2].synchronize()                              # D2H of the previous window has landed
+        return prev[0], tuple(self.h_out[prev[1]])
 
     def flush(self):
         return self._collect()
@@ -294,8 +300,8 @@ def _stream(imDir, fileList, fileType, ndim, dims, sig, NtChunk, NtSlice, starts
         tstr = str(centre).zfill(4)
         for nm, a in zip(names, arrs):
             out = a
-            if ndim == 3 and nm == 'rel' and precision == 'fp64':
-                out = a.astype(np.float32)             # dtype the reference writes (calc_flow.py:355-357, :529)
+            if ndim == 3 and nm == 'rel':
+                out = a.astype(np.float32, copy=False) # dtype the reference writes (calc_flow.py:355-357, :529)
             tiffio.imwrite(str(savedir / name) + '_' + nm + '_t' + tstr + '.tiff', out, photometric='minisblack')
         if verbose:
             print(str(datetime.now()) + ' - Frame ' + str(centre) + ' saved.  Duration: ' + str(datetime.now() - t_start[centre]))

@@ -323,3 +323,25 @@ def test_misaligned_device_buffers_are_rejected():
     rc = ctx.lib.of3d_flow3d(ctx.handle, C.c_void_p(raw.data_ptr()), _lib.U16, _lib.DEVICE, 7, 4, 8, 8, C.byref(taps), _lib.FP64, 0,
                              C.c_void_p(outs[0].data_ptr() + 4), *[C.c_void_p(o.data_ptr()) for o in outs[1:]], _lib.DEVICE)
     assert rc == -1 and 'aligned' in _lib.last_error()
+
+
+def test_rel_f32_flag_is_one_rounding_of_the_float64_value():
+    """OF3D_FLAG_REL_F32 (default 3D return dtype): the device narrows the float64 reliability once -- identical to
+    rounding rel_dtype='float64' on the host; out= buffers choose the dtype themselves."""
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 3000, (7, 10, 40, 70)).astype(np.uint16)
+    cf = _cf()
+    r64 = cf.calc_flow3D(img, 2, 1, 2, rel_dtype='float64')
+    r32 = cf.calc_flow3D(img, 2, 1, 2)
+    assert r32[3].dtype == np.float32 and r64[3].dtype == np.float64
+    assert np.array_equal(r32[3], r64[3].astype(np.float32))
+    assert all(np.array_equal(a, b) for a, b in zip(r32[:3], r64[:3]))
+    out = tuple(np.empty(img.shape[1:], np.float64) for _ in range(3)) + (np.empty(img.shape[1:], np.float32),)
+    got = cf.calc_flow3D(img, 2, 1, 2, out=out)
+    assert got[3] is out[3] and np.array_equal(out[3], r32[3]) and np.array_equal(out[0], r64[0])
+    out64 = tuple(np.empty(img.shape[1:], np.float64) for _ in range(4))
+    cf.calc_flow3D(img, 2, 1, 2, out=out64)
+    assert np.array_equal(out64[3], r64[3])
+    import torch
+    t32 = cf.calc_flow3D(torch.from_numpy(img).cuda(), 2, 1, 2)
+    assert t32[3].dtype == torch.float32 and np.array_equal(t32[3].cpu().numpy(), r32[3])
