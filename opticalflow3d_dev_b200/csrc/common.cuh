@@ -118,8 +118,20 @@ static inline int window_class(const of3d_taps* t) {
         if (t->nW <= ks[i]) return i;
     return -1;
 }
-static inline bool fast_supported(const of3d_taps* t) { return spatial_class(t) >= 0 && window_class(t) >= 0; }
+// The marching kernels read only half of every (anti)symmetric filter: S, G, W symmetric and D antisymmetric, bit for bit
+// (true of the reference's sampled Gaussians, calc_flow.py:238-266; arbitrary taps run on the generic kernels)
+static inline bool taps_symmetric(const double* w, int n, double sign) {
+    for (int i = 0; i < n / 2; ++i)
+        if (w[n - 1 - i] != sign * w[i]) return false;
+    return true;
+}
+static inline bool fast_supported(const of3d_taps* t) {
+    return spatial_class(t) >= 0 && window_class(t) >= 0 && taps_symmetric(t->S, t->nS, 1.0) && taps_symmetric(t->G, t->nG, 1.0) &&
+           taps_symmetric(t->W, t->nW, 1.0) && taps_symmetric(t->D, t->nD, -1.0);
+}
 // workspace volumes of compute type used by run_fast (excluding ic and dt0)
 static inline int fast_volumes(int ndim) { return ndim == 3 ? 9 + 4 : 3; }
+// the gradient volumes carry up to kMaxZPad replicated planes beyond each z face for the TMA-fed window march
+constexpr int kMaxZPad = 12;
 
 }  // namespace of3d

@@ -82,16 +82,30 @@ struct Prefetcher {
     __device__ __forceinline__ T read(const int slot, const int i) const { return lbase[(slot * NIN + i) * 32]; }
 };
 
+// The scatter FMAs are volatile asm so that their program order survives: left to itself ptxas re-associates the fully
+// unrolled scatter into a GATHER -- it keeps the last K inputs in registers and evaluates every output as one chain of
+// K dependent FMAs at the step where it completes, which is latency-bound (one DFMA per ~8 cycles per warp) instead of
+// K independent FMAs per step.
+__device__ __forceinline__ void fma_acc(double& acc, double w, double v) { asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc) : "d"(w), "d"(v)); }
+__device__ __forceinline__ void fma_acc(float& acc, float w, float v) { asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc) : "f"(w), "f"(v)); }
+__device__ __forceinline__ void mul_acc(double& acc, double w, double v) { asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(acc) : "d"(w), "d"(v)); }
+__device__ __forceinline__ void mul_acc(float& acc, float w, float v) { asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(acc) : "f"(w), "f"(v)); }
+
 // One scatter step at static phase PH of an unrolled period P: input v (position p = o + R for the
 // output o that completes now) is accumulated into the K outputs it touches.  Returns the completed sum.
-template <typename T, int K, int P>
+// SYM = +1 / -1: the taps are (anti)symmetric, w[K-1-k] = +-w[k] (checked by the host, fast_supported): only the first
+// R + 1 of them are read, which halves the registers the taps occupy.
+template <typename T, int K, int P, int SYM = 0>
 __device__ __forceinline__ T ring_push(T (&acc)[P], const Taps<T, K>& f, const T v, const int ph) {
     constexpr int R = K / 2;
+    const T vn = SYM < 0 ? -v : v;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int slot = (ph + R - k + 2 * P) % P;   // constant after unrolling
-        if (k == 0) acc[slot] = f.w[0] * v;
-        else acc[slot] = fma(f.w[k], v, acc[slot]);
+        const bool mirror = SYM != 0 && k > R;
+        const T w = f.w[mirror ? K - 1 - k : k];
+        if (k == 0) mul_acc(acc[slot], w, v);
+        else fma_acc(acc[slot], w, mirror ? vn : v);
     }
     return acc[(ph - R + 2 * P) % P];
 }
@@ -184,7 +198,7 @@ __global__ void __launch_bounds__(WPB * 32) march_window(const WindowArgs<T, K> 
             cp_async_wait<DEPTH - 2>();            // step s+1 has landed
             vn0 = pre.read((ph + 1) % DEPTH, 0);
             vn1 = pre.read((ph + 1) % DEPTH, 1);
-            const T res = ring_push<T, K, P>(acc, a.f, v, ph);
+            const T res = ring_push<T, K, P, 1>(acc, a.f, v, ph);
             if ((unsigned)(s0 + ph - 2 * R) < nvalid) *reinterpret_cast<T*>(optr) = res;
             optr += pre.stride_bytes;
         }
@@ -202,12 +216,15 @@ struct PairArgs {
     Taps<T, K> f0, f1;
     const T* in[2];
     T* out[2];
+    int pad;          // > 0: also write `pad` copies of the first / last output plane beyond the z faces (the outputs
+                      // are then volumes with pad extra planes on either side; see kernels_tma.cuh)
 };
 
 template <typename T, int DEPTH, int WPB>
 constexpr size_t pair_smem() { return (size_t)WPB * Prefetcher<T, 2, DEPTH>::elems_per_warp * sizeof(T); }
 
-template <typename T, int K, int P, int DEPTH, int WPB>
+// SYM0 / SYM1: symmetry of f0 / f1 (+1 symmetric, -1 antisymmetric)
+template <typename T, int K, int P, int DEPTH, int WPB, int SYM0, int SYM1>
 __global__ void __launch_bounds__(WPB * 32) march_pair(const PairArgs<T, K> a) {
     static_assert(P >= K && P % DEPTH == 0, "bad unroll period");
     constexpr int R = K / 2;
@@ -261,8 +278,8 @@ __global__ void __launch_bounds__(WPB * 32) march_pair(const PairArgs<T, K> a) {
             cp_async_wait<DEPTH - 2>();            // step s+1 has landed: read it while step s is accumulated
             vn0 = pre.read((ph + 1) % DEPTH, 0);
             vn1 = pre.read((ph + 1) % DEPTH, 1);
-            const T r0 = ring_push<T, K, P>(acc0, a.f0, v0, ph);
-            const T r1 = ring_push<T, K, P>(acc1, a.f1, v1, ph);
+            const T r0 = ring_push<T, K, P, SYM0>(acc0, a.f0, v0, ph);
+            const T r1 = ring_push<T, K, P, SYM1>(acc1, a.f1, v1, ph);
             if ((unsigned)(s0 + ph - 2 * R) < nvalid) {
                 *reinterpret_cast<T*>(reinterpret_cast<char*>(a.out[0]) + ooff) = r0;
                 *reinterpret_cast<T*>(reinterpret_cast<char*>(a.out[1]) + ooff) = r1;
@@ -271,6 +288,20 @@ __global__ void __launch_bounds__(WPB * 32) march_pair(const PairArgs<T, K> a) {
         }
     }
     cp_async_wait<0>();
+    // replicated planes beyond the z faces (each lane copies the values it stored itself)
+    if (a.pad > 0 && lane_ok) {
+#pragma unroll 1
+        for (int face = 0; face < 2; ++face) {
+            if (face == 0 ? c0 != 0 : c1 != (int)g.n_march) continue;
+            const int64_t z = face == 0 ? 0 : g.n_march - 1, dir = face == 0 ? -1 : 1;
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {
+                T* o = a.out[q] + base + z * g.stride_march;
+                const T v = *o;
+                for (int j = 1; j <= a.pad; ++j) o[dir * j * g.stride_march] = v;
+            }
+        }
+    }
 }
 
 }  // namespace of3d

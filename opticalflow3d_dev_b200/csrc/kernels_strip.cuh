@@ -179,11 +179,11 @@ __device__ __forceinline__ void strip_grad_body(const GradStripArgs<T, KR, KS>& 
                 const int s = s0 + ph;
                 const T v = st.gathered(r);
                 T resA;
-                if (ROLE == 2) resA = ring_push<T, KS, P>(accA, a.fS, v, ph);
-                else resA = ring_push<T, KR, P>(accA, fyA, v, ph);
+                if (ROLE == 2) resA = ring_push<T, KS, P, 1>(accA, a.fS, v, ph);
+                else resA = ring_push<T, KR, P, (ROLE == 0 ? 1 : -1)>(accA, fyA, v, ph);
                 if ((unsigned)(s - lagA) < nvalid) oA[(int64_t)(m0 + s - lagA) * g.stride_m] = resA;
                 if (ROLE == 1) {
-                    const T resB = ring_push<T, KS, P>(*reinterpret_cast<T(*)[P]>(accB), a.fS, v, ph);
+                    const T resB = ring_push<T, KS, P, 1>(*reinterpret_cast<T(*)[P]>(accB), a.fS, v, ph);
                     if (oB && (unsigned)(s - R - RS) < nvalid) oB[(int64_t)(m0 + s - R - RS) * g.stride_m] = resB;
                 }
             }
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const 
                 T* pk = m_dst + (b & 1) * RB * PARKROW;
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
-                    const T res = ring_push<T, K, P>(acc, a.f, st.gathered(r), bi * RB + r);
+                    const T res = ring_push<T, K, P, 1>(acc, a.f, st.gathered(r), bi * RB + r);
                     constexpr int kBias = (2 * R + RB - 1) / RB * RB;
                     pk[((r + kBias - 2 * R) % RB) * PARKROW] = res;
                 }

@@ -1,0 +1,161 @@
+// TMA-fed marching kernels for sm_100a.  Internal header.
+//
+// The cp.async (LDGSTS) marches of kernels_march.cuh pay 8 LSU cycles per 32-lane load instruction and every channel
+// re-fetches the gradient rows it shares with other channels: the products + window-z march ran at 83 % L1/LSU
+// utilisation with the FP64 pipe 62 % busy.  Here one block owns (y row, 64 x columns) for ALL nine channels: the
+// tile {64 x, 1 y, ZT z, 4 gradient volumes} of a stage is fetched ONCE per block by one tensor-map copy
+// (cp.async.bulk.tensor, the TMA engine: no LSU instruction per lane, no L1 wavefronts) into a shared-memory ring of
+// STAGES stages, completion tracked by an mbarrier transaction count; the channel warps wait on the stage's "full"
+// barrier, march ZT steps out of shared memory and release the stage on its "empty" barrier.
+// TMA fills out-of-range elements with zeros, scipy's mode='nearest' wants the edge plane: the gradient volumes
+// therefore carry R replicated planes beyond each z face (written by march_pair), so every tile is in range in z.
+// (Row-by-row cp.async.bulk copies with clamped addresses were tried first: 64 copies of 256 B per stage ran at
+// ~80 cycles per copy, 0.9 TB/s over the chip.)
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "kernels_march.cuh"
+
+namespace of3d {
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// one 4-D tile global -> shared through a tensor map, completion (box bytes) on `bar`
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int x, int y, int z, int v, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(v), "r"(bar) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Products + window z pass (calc_flow.py:300-313, z passes), all nine channels of a (y, 64 x) column per block:
+// 18 marching warps (channel ch = warp % 9 of 32-column group warp / 9) + one producer warp.  The producer loop lives in
+// a __noinline__ function: inlined anywhere in the kernel it makes ptxas move the taps from uniform registers to 50
+// vector registers (168 registers unbounded, spills at the 96 the block size allows).
+constexpr int kTmaZT = 8;        // z steps per stage
+constexpr int kTmaStages = 4;
+constexpr int kTmaGroups = 2;    // 32-column groups per block
+constexpr int kTmaWarps = 9 * kTmaGroups + 1;
+constexpr int kTmaTX = 32 * kTmaGroups;
+
+template <typename T>
+constexpr size_t window_tma_smem() { return (size_t)kTmaStages * 4 * kTmaZT * kTmaTX * sizeof(T) + 2 * kTmaStages * 8; }
+
+// One block per (y, column group, z chunk) task.  (Persistent blocks striding over the tasks, so that the ring never
+// drains between tasks, and a 6-stage ring were measured 3 % slower: the task bookkeeping costs registers the marching
+// loop spills for.)
+struct TmaTask {
+    int x0, y, c0, nout, nstages;
+};
+template <int K>
+__device__ __forceinline__ TmaTask tma_task(int n_chunks, int lane_groups, int chunk_len, int n_march, int task) {
+    TmaTask t;
+    const int chunk = task % n_chunks; task /= n_chunks;
+    const int ngrp = (lane_groups + kTmaGroups - 1) / kTmaGroups;
+    t.x0 = (task % ngrp) * kTmaTX;
+    t.y = task / ngrp;
+    t.c0 = chunk * chunk_len;
+    t.nout = min(t.c0 + chunk_len, n_march) - t.c0;
+    t.nstages = (t.nout + 2 * (K / 2) + kTmaZT - 1) / kTmaZT;
+    return t;
+}
+
+template <typename T, int K>
+__device__ __noinline__ void window_tma_producer(const CUtensorMap* tmap, int n_chunks, int lane_groups, int chunk_len, int n_march,
+                                                 uint32_t ring_s, uint32_t bar_s) {
+    constexpr int ZT = kTmaZT, ST = kTmaStages;
+    constexpr uint32_t kStageBytes = 4 * ZT * kTmaTX * sizeof(T);
+    if ((threadIdx.x & 31) != 0) return;
+    const TmaTask t = tma_task<K>(n_chunks, lane_groups, chunk_len, n_march, blockIdx.x);
+    for (int it = 0; it < t.nstages; ++it) {
+        const int slot = it % ST;
+        if (it >= ST) mbar_wait(bar_s + 8 * (ST + slot), ((it / ST) - 1) & 1);       // every marching warp released the slot
+        mbar_arrive_expect_tx(bar_s + 8 * slot, kStageBytes);
+        // logical z of the first input is c0 - R; the padded volume starts at logical -R
+        tma_load_4d(ring_s + slot * kStageBytes, tmap, t.x0, t.y, t.c0 + it * ZT, 0, bar_s + 8 * slot);
+    }
+}
+
+// tmap: {x, y, z + 2R planes, 4 volumes} over the padded gradient volumes {dt, dx, dy, dz}, box {64, 1, ZT, 4}
+template <typename T, int K, int P>
+__global__ void __launch_bounds__(kTmaWarps * 32, 1) march_window_tma(const WindowArgs<T, K> a, const __grid_constant__ CUtensorMap tmap) {
+    static_assert(P >= K && P % kTmaZT == 0, "bad unroll period");
+    constexpr int R = K / 2, ZT = kTmaZT, ST = kTmaStages, NG = kTmaGroups, TX = kTmaTX;
+    constexpr int kStageElems = 4 * ZT * TX;                 // [volume][z][x]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* ring = reinterpret_cast<T*>(smem_raw);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t bar_s = ring_s + (uint32_t)(ST * kStageElems * sizeof(T));   // full[ST], empty[ST]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const MarchGeom& g = a.g;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < ST; ++i) { mbar_init(bar_s + 8 * i, 1); mbar_init(bar_s + 8 * (ST + i), 9 * NG); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 9 * NG) {
+        window_tma_producer<T, K>(&tmap, g.n_chunks, g.lane_groups, g.chunk, (int)g.n_march, ring_s, bar_s);
+        return;
+    }
+
+    // ---- marching warps
+    const int ch = warp % 9, grp = warp / 9;
+    // channel -> gradient pair {xx,xy,xz,yy,yz,zz,tx,ty,tz} over {dt,dx,dy,dz}
+    const int ia = ch < 3 ? 1 : (ch < 5 ? 2 : (ch == 5 ? 3 : ch - 5));
+    const int ib = ch < 3 ? ch + 1 : (ch < 5 ? ch - 1 : (ch == 5 ? 3 : 0));
+    const T* sa = ring + (ia * ZT) * TX + grp * 32 + lane;
+    const T* sb = ring + (ib * ZT) * TX + grp * 32 + lane;
+    const int64_t stride_bytes = g.stride_march * (int64_t)sizeof(T);
+
+    T acc[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) acc[i] = T(0);
+
+    const TmaTask t = tma_task<K>(g.n_chunks, g.lane_groups, g.chunk, (int)g.n_march, blockIdx.x);
+    const int64_t lane0 = (int64_t)t.x0 + grp * 32;
+    const unsigned nvalid = lane0 + lane < g.n_lane ? (unsigned)t.nout : 0u;
+    // store position of the output completed at step s: c0 + s - 2R
+    char* optr = reinterpret_cast<char*>(a.out + (int64_t)ch * g.vol + (int64_t)t.y * g.stride_other + lane0 + lane) +
+                 ((int64_t)t.c0 - 2 * R) * stride_bytes;
+    int it = 0;
+#pragma unroll 1
+    for (int s0 = 0;; s0 += P) {
+#pragma unroll
+        for (int sg = 0; sg < P / ZT; ++sg) {
+            const int slot = it % ST;
+            mbar_wait(bar_s + 8 * slot, (it / ST) & 1);
+            const T* pa = sa + slot * kStageElems;
+            const T* pb = sb + slot * kStageElems;
+#pragma unroll
+            for (int r = 0; r < ZT; ++r) {
+                const int ph = sg * ZT + r;
+                const T v = pa[r * TX] * pb[r * TX];
+                const T res = ring_push<T, K, P, 1>(acc, a.f, v, ph);
+                if ((unsigned)(s0 + ph - 2 * R) < nvalid) *reinterpret_cast<T*>(optr) = res;
+                optr += stride_bytes;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_s + 8 * (ST + slot));
+            if (++it >= t.nstages) return;
+        }
+    }
+}
+
+}  // namespace of3d

@@ -81,13 +81,14 @@ static int ws_ensure(of3d_ctx* c, size_t bytes) {
 // Volumes of compute type needed by the generic pipeline (see run_generic)
 static int generic_volumes(int ndim) { return ndim == 3 ? 2 + 2 + 4 + 1 + 9 : 2 + 2 + 3 + 1 + 5; }
 
-static size_t plan_bytes(int ndim, int64_t kt, int64_t n, int in_dtype, int precision, int in_mem, int out_mem) {
+static size_t plan_bytes(int ndim, int64_t kt, int64_t n, int64_t plane, int in_dtype, int precision, int in_mem, int out_mem) {
     const size_t ts = precision == OF3D_FP32 ? 4 : 8;
     size_t b = 0;
     b += (size_t)std::max(generic_volumes(ndim), 2 + fast_volumes(ndim)) * align_up((size_t)n * ts);
     if (in_mem == OF3D_HOST) b += (size_t)kt * align_up((size_t)n * dtype_size(in_dtype));
     if (out_mem == OF3D_HOST) b += (size_t)(ndim + 1) * align_up((size_t)n * ts);
     if (precision == OF3D_FP64) b += align_up((size_t)n * 8);     // float64 reliability scratch of OF3D_FLAG_REL_F32
+    if (ndim == 3) b += (size_t)4 * 2 * kMaxZPad * (size_t)plane * ts + 4096;   // replicated edge planes of the gradient volumes
     return b + 4096;
 }
 
@@ -279,7 +280,7 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
     const Shape s{ndim, nz, ny, nx};
     const int64_t n = s.n();
     const size_t ts = precision == OF3D_FP32 ? 4 : 8;
-    if (int rc = ws_ensure(c, plan_bytes(ndim, stage == 2 ? 0 : t->nT, n, in_dtype, precision, stage == 2 ? OF3D_DEVICE : in_mem,
+    if (int rc = ws_ensure(c, plan_bytes(ndim, stage == 2 ? 0 : t->nT, n, ny * nx, in_dtype, precision, stage == 2 ? OF3D_DEVICE : in_mem,
                                          stage == 1 ? OF3D_DEVICE : out_mem))) return rc;
     c->ws_off = 0;
 
@@ -442,7 +443,7 @@ OF3D_API int of3d_destroy(of3d_ctx* c) {
 OF3D_API size_t of3d_workspace_bytes(int ndim, int64_t nt_taps, int64_t nz, int64_t ny, int64_t nx, int in_dtype, int precision,
                             int in_mem, int out_mem) {
     if (ndim != 2 && ndim != 3) return 0;
-    return plan_bytes(ndim, nt_taps, nz * ny * nx, in_dtype, precision, in_mem, out_mem);
+    return plan_bytes(ndim, nt_taps, nz * ny * nx, ny * nx, in_dtype, precision, in_mem, out_mem);
 }
 
 OF3D_API int of3d_reserve(of3d_ctx* c, size_t bytes) {

@@ -2,7 +2,7 @@
 import csv, collections, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[1]; idx = {h: i for i, h in enumerate(hdr)}
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) == len(hdr) and r[0] != 'Address']
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
 tot = collections.Counter(); byop = collections.Counter(); execs = collections.Counter(); total = 0
 for r in data:
