@@ -230,24 +230,26 @@ constexpr size_t strip_smem() {
     return (size_t)(NCH * NHALF * StripStage<T, K, PROD ? 2 : 1>::elems + 2 * kStripRB * strip_parkrow<NCH, NHALF>()) * sizeof(T);
 }
 
-// solve units (32 voxels each) of warp `warp`; returns how many
+// ui-th solve unit (32 voxels) of warp `warp` or -1; recomputed at every use (a table indexed by ui lives in local
+// memory -- its loads were 5 % of the kernel's stall samples -- and four registers per thread are not to spare)
 template <int NCH, int NHALF>
-__device__ __forceinline__ int solve_units(int warp, int (&su)[4]) {
+__device__ __forceinline__ int solve_unit(int warp, int ui) {
     const int q = warp >> 2, sm = warp & 3;            // q-th warp of scheduler sm
-    int n = 0;
-    if (NCH == 9 && NHALF == 2) {                      // 18 warps (5,5,4,4), 16 units: 3,3,5,5
-        if (sm >= 2) { su[n++] = (sm - 2) * 5 + q; if (q == 0) su[n++] = (sm - 2) * 5 + 4; }
-        else if (q < 3) su[n++] = 10 + sm * 3 + q;
+    if (NCH == 9 && NHALF == 2) {                      // 18 warps (5,5,4,4), 16 units: 3,3,5,5 (one unit per warp --
+                                                       // 4,4,4,4 -- measured 15 % slower: the 5-warp schedulers bind)
+        if (sm >= 2) return ui == 0 ? (sm - 2) * 5 + q : ((ui == 1 && q == 0) ? (sm - 2) * 5 + 4 : -1);
+        return (ui == 0 && q < 3) ? 10 + sm * 3 + q : -1;
     } else if (NCH == 9 && NHALF == 1) {               // 9 warps (3,2,2,2), 8 units: 0,3,3,2
-        if (sm == 1) { su[n++] = q; if (q == 0) su[n++] = 2; }
-        else if (sm == 2) { su[n++] = 3 + q; if (q == 0) su[n++] = 5; }
-        else if (sm == 3) su[n++] = 6 + q;
+        if (sm == 1) return ui == 0 ? q : ((ui == 1 && q == 0) ? 2 : -1);
+        if (sm == 2) return ui == 0 ? 3 + q : ((ui == 1 && q == 0) ? 5 : -1);
+        if (sm == 3) return ui == 0 ? 6 + q : -1;
+        return -1;
     } else if (NCH == 5 && NHALF == 2) {               // 10 warps (3,3,2,2), 16 units: 0,0,8,8
-        if (sm >= 2) for (int i = 0; i < 4; ++i) su[n++] = (sm - 2) * 8 + q * 4 + i;
+        return (sm >= 2 && ui < 4) ? (sm - 2) * 8 + q * 4 + ui : -1;
     } else {                                           // generic: round robin
-        for (int u = warp; u < kStripRB * NHALF; u += NCH * NHALF) if (n < 4) su[n++] = u;
+        const int u = warp + ui * NCH * NHALF;
+        return u < kStripRB * NHALF ? u : -1;
     }
-    return n;
 }
 
 template <typename T, int K, int P, int NCH, int NHALF, bool PROD>
@@ -286,9 +288,6 @@ __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const 
         st.src[0] = a.in[0] + (int64_t)o * g.stride_o + (int64_t)ch * g.vol;
     }
     T* const m_dst = park + ch * TX + 32 * half + lane;
-    int su[4] = {-1, -1, -1, -1};
-    const int nsu = solve_units<NCH, NHALF>(warp, su);
-
     T acc[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) acc[i] = T(0);
@@ -317,8 +316,10 @@ __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const 
             __syncthreads();                                                  // one batch of outputs parked by all channels
             // ---------------- solve the RB x TX outputs of batch b
 #pragma unroll 1
-            for (int ui = 0; ui < nsu; ++ui) {
-                const int v = su[ui] * 32 + lane;                             // voxel of the batch: row v / TX, column v % TX
+            for (int ui = 0; ui < 4; ++ui) {
+                const int unit = solve_unit<NCH, NHALF>(warp, ui);
+                if (unit < 0) break;
+                const int v = unit * 32 + lane;                               // voxel of the batch: row v / TX, column v % TX
                 const int s_i = v / TX, s_col = v % TX;
                 const int s_c = cs0 + s_col;
                 const int j = b * RB - 2 * R + s_i;

@@ -43,8 +43,9 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
 // so the root is found instead on the shifted cubic: with s = t + 1/2 in [-1/2, 0] and e = 1 - r in [0, 2],
 //     s^2 (4s - 6) + e = 0 .
 // The seed is the fp32 fixed-point iterate of s = -sqrt(e / (6 - 4s)) (contraction rate < 0.19, exact as
-// e -> 0; relative error < 6e-3 after two rounds), polished by three Newton steps in fp64 whose slope
-// reciprocal only needs fp32 accuracy because Newton is self-correcting.  In this form the convergence is
+// e -> 0; relative error < 6e-3 after two rounds), polished by two Newton steps in fp32 and ONE in fp64 whose
+// slope reciprocal only needs fp32 accuracy because Newton is self-correcting.  (Three fp64 Newton steps were the
+// longest part of the per-voxel dependency chain; the solve is latency-bound inside strip_window_solve.)  In this form the convergence is
 // quadratic in the RELATIVE error of s, also next to the double root (two equal smallest eigenvalues, e -> 0)
 // where the trigonometric form loses half the digits.  The whole function is straight-line code (selects
 // instead of branches).
@@ -67,12 +68,18 @@ __device__ __forceinline__ double min_eig_sym3(double xx, double xy, double xz, 
         const float d = 6.0f - 4.0f * sf;            // in [6, 8]
         sf = -ef * rsqrtf(ef * d);                   // -sqrt(e/d)
     }
-    double s = (double)sf;
+    // two Newton steps in fp32 (FP32 pipe, off the FP64 dependency chain): relative error ~1e-7
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
+    for (int it = 0; it < 2; ++it) {
+        const float f = fmaf(sf * sf, fmaf(4.0f, sf, -6.0f), ef);
+        const float fp = 12.0f * sf * (sf - 1.0f);   // > 0 for s < 0
+        sf = fminf(-0.0f, sf - f * __frcp_rn(fmaxf(fp, 1e-30f)));
+    }
+    double s = (double)sf;
+    {   // one Newton step in fp64: quadratic convergence takes 1e-7 to ~1e-14
         const double f = s * s * (4.0 * s - 6.0) + e;
-        const double fp = 12.0 * s * (s - 1.0);      // > 0 for s < 0
-        s -= f * (double)__frcp_rn((float)fp);
+        const double fp = 12.0 * s * (s - 1.0);
+        s -= f * (double)__frcp_rn(fmaxf((float)fp, 1e-30f));
     }
     s = fmin(0.0, fmax(-0.5, s));
     const double lam = (q - p) + 2.0 * p * s;
