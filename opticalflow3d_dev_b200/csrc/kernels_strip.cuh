@@ -40,12 +40,14 @@ struct StripGeom {
 };
 
 // Warp-private staging: one or two row buffers (blocked-transposed) and the gathered rows
-template <typename T, int KG, int NIN>
+// (NBUF = 2: two batches of rows in flight -- the HBM-bound gradient stage needs the deeper prefetch)
+template <typename T, int KG, int NIN, int NBUF = 1>
 struct StripStage {
     static constexpr int ROWLEN = strip_rowlen<KG>(), PITCH = strip_pitch<KG>(), ROWSTRIDE = strip_rowstride<KG>();
     static constexpr int NLOAD = (ROWLEN + 7) / 8;
-    static constexpr int elems = NIN * kStripRB * ROWSTRIDE + kStripRB * kXwRow;
-    T* rows;                // [NIN][RB][ROWSTRIDE]
+    static constexpr int BUF = NIN * kStripRB * ROWSTRIDE;
+    static constexpr int elems = NBUF * BUF + kStripRB * kXwRow;
+    T* rows;                // [NBUF][NIN][RB][ROWSTRIDE]; batch b lives in buffer b % NBUF
     T* xw;                  // [RB][kXwRow]
     uint32_t rows_s;
     const T* src[NIN];      // plane base of each input (already offset to z and channel)
@@ -55,7 +57,7 @@ struct StripStage {
 
     __device__ __forceinline__ void init(T* smem_warp, int cw0, int m_first, const StripGeom& g) {
         rows = smem_warp;
-        xw = smem_warp + NIN * kStripRB * ROWSTRIDE;
+        xw = smem_warp + NBUF * BUF;
         rows_s = (uint32_t)__cvta_generic_to_shared(rows);
         const int lane = threadIdx.x & 31;
         c0 = cw0 - KG / 2 + (lane & 7);
@@ -69,7 +71,7 @@ struct StripStage {
         for (int p = 0; p < 2; ++p) {
             const int r = lrr + 4 * p;
             const int m = max(0, min(mfirst + b * kStripRB + r, nmm1));
-            const uint32_t dst = rows_s + (uint32_t)((r * ROWSTRIDE + l8 * PITCH) * sizeof(T));
+            const uint32_t dst = rows_s + (uint32_t)(((b % NBUF) * BUF + r * ROWSTRIDE + l8 * PITCH) * sizeof(T));
 #pragma unroll
             for (int i = 0; i < NLOAD; ++i) {
                 if (ROWLEN % 8 == 0 || l8 + 8 * i < ROWLEN) {
@@ -85,10 +87,10 @@ struct StripStage {
     // gather with filter f (KF <= KG taps, centred in the loaded halo) of input q (or the product of inputs 0 and 1),
     // result to xw
     template <int KF, bool PROD>
-    __device__ __forceinline__ void gather(const Taps<T, KF>& f, int q) {
+    __device__ __forceinline__ void gather(const Taps<T, KF>& f, int q, int b = 0) {
         constexpr int XB = kStripXB, OFF = (KG - KF) / 2;
         const int lane = threadIdx.x & 31, g_r = lane >> 2, g_b = lane & 3;
-        const T* s0 = rows + (q * kStripRB + g_r) * ROWSTRIDE + g_b;
+        const T* s0 = rows + (b % NBUF) * BUF + (q * kStripRB + g_r) * ROWSTRIDE + g_b;
         T ga[XB];
 #pragma unroll
         for (int i = 0; i < XB; ++i) ga[i] = T(0);
@@ -127,7 +129,7 @@ struct GradStripArgs {
 };
 
 template <typename T, int KR>
-constexpr size_t grad_strip_smem(int wpb) { return (size_t)wpb * StripStage<T, KR, 1>::elems * sizeof(T); }
+constexpr size_t grad_strip_smem(int wpb) { return (size_t)wpb * StripStage<T, KR, 1, 2>::elems * sizeof(T); }
 
 // One role.  Each role is its own kernel instantiation: dispatched inside one kernel the three bodies get a merged
 // register allocation of 228 registers (8 warps per SM); separately they need 56-95.
@@ -137,7 +139,7 @@ __device__ __forceinline__ void strip_grad_body(const GradStripArgs<T, KR, KS>& 
     constexpr int KGATHER = ROLE == 1 ? KS : KR;            // taps of the x filter
     constexpr int KA = ROLE == 2 ? KS : KR;                 // taps of the (first) y filter
     constexpr int lagA = R + KA / 2;                        // the stream with radius rf completes row m0 + s - R - rf
-    using Stage = StripStage<T, KR, 1>;
+    using Stage = StripStage<T, KR, 1, 2>;
     const StripGeom& g = a.g;
     const int lane = threadIdx.x & 31;
     const int cw0 = strip * 32;
@@ -161,18 +163,19 @@ __device__ __forceinline__ void strip_grad_body(const GradStripArgs<T, KR, KS>& 
     for (int i = 0; i < (ROLE == 1 ? P : 1); ++i) accB[i] = T(0);
 
     st.issue(0);
+    st.issue(1);
     int b = 0;
 #pragma unroll 1
     for (int s0 = 0; s0 < nsteps; s0 += P) {
 #pragma unroll
         for (int bi = 0; bi < P / RB; ++bi, ++b) {
-            cp_async_wait<0>();
+            cp_async_wait<1>();                                               // batch b has landed, b + 1 is in flight
             __syncwarp();
-            if (ROLE == 0) st.template gather<KR, false>(a.fG, 0);
-            else if (ROLE == 1) st.template gather<KS, false>(a.fS, 0);
-            else st.template gather<KR, false>(a.fD, 0);
+            if (ROLE == 0) st.template gather<KR, false>(a.fG, 0, b);
+            else if (ROLE == 1) st.template gather<KS, false>(a.fS, 0, b);
+            else st.template gather<KR, false>(a.fD, 0, b);
             __syncwarp();
-            st.issue(b + 1);
+            st.issue(b + 2);                                                  // into the buffer just consumed
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
                 const int ph = bi * RB + r;
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(WPB * 32) strip_grad(const GradStripArgs<T, KR
     const int strip = (int)(task % nstrips); task /= nstrips;
     const int chunk = (int)(task % g.n_chunks);
     const int o = (int)(task / g.n_chunks);
-    strip_grad_body<T, KR, KS, P, ROLE>(a, reinterpret_cast<T*>(smem_raw) + warp * StripStage<T, KR, 1>::elems, strip, chunk, o);
+    strip_grad_body<T, KR, KS, P, ROLE>(a, reinterpret_cast<T*>(smem_raw) + warp * StripStage<T, KR, 1, 2>::elems, strip, chunk, o);
 }
 
 // ------------------------------------------------------------------------------------------------
