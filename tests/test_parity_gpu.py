@@ -351,6 +351,7 @@ def test_rel_f32_flag_is_one_rounding_of_the_float64_value():
 def test_tma_window_march_equals_cp_async_march(precision, monkeypatch):
     """The TMA-fed window z march (tensor-map tiles, padded gradient volumes) and the cp.async march it replaces do the
     same arithmetic in the same order: bit-identical results.  Columns: one full 64-column block, one partial group."""
+    from opticalflow3d_dev_b200.synth import make_stack
     img = make_stack((7, 21, 50, 200), seed=99, dtype=np.uint16)
     cf = _cf()
     monkeypatch.delenv('OF3D_NO_TMA', raising=False)
