@@ -342,6 +342,8 @@ def gpu_arm(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    from opticalflow3d_dev_b200 import numa
+    cpus = numa.bind_to_device(local_rank) if world > 1 else None   # pinned buffers and copy threads on the GPU's NUMA node
     w = WORKLOADS[args.workload]
     shape, sig = tuple(w['shape']), w['sig']
     ndim = len(shape) - 1
@@ -430,7 +432,7 @@ def gpu_arm(args, rank, world, local_rank):
         from opticalflow3d_dev_b200.timelapse import FlowStream
         n_e2e = max(1, min(args.e2e_timepoints, len(mine))) if mine else 0
         np_odt = np.float64 if args.precision == 'fp64' else np.float32
-        call_rate = None
+        call_rate = call_rate_pageable = None
         if n_e2e:
             nfr = n_e2e + 2 * rt + 2                             # frames fed to the stream: 2 warm-up windows + n_e2e timed
             nfr = min(nfr, nloc)
@@ -461,6 +463,14 @@ def gpu_arm(args, rank, world, local_rank):
             tc = time.perf_counter()
             fn(hfr[1:1 + kt], *sig, **kw)
             call_rate = vol / (time.perf_counter() - tc)
+            # the same call with ordinary (pageable) NumPy arrays in and out: what a script written for the reference does
+            pg = np.array(hfr[0:kt + 1])
+            kw2 = dict(precision=args.precision, device=local_rank, generic=args.generic)
+            r_ = fn(pg[0:kt], *sig, **kw2); del r_
+            tc = time.perf_counter()
+            r_ = fn(pg[1:1 + kt], *sig, **kw2)
+            call_rate_pageable = vol / (time.perf_counter() - tc)
+            del r_, pg
         else:
             h2d = d2h = 0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -471,8 +481,10 @@ def gpu_arm(args, rank, world, local_rank):
                'h2d_bytes_per_step': int(nn[1].item()), 'd2h_bytes_per_step': int(nn[2].item()),
                'timepoints': int(nn[0].item()),
                'api': 'timelapse.FlowStream.push(host frame) -> host (vx,vy,vz,rel), pinned; the engine under process_flow',
+               'numa_bound_cpus': (len(cpus) if cpus else None),
                'calc_flow_call_value': call_rate,
-               'calc_flow_call_api': 'calc_flow%dD(host ndarray window) -> host ndarrays (pinned), rank 0' % ndim}
+               'calc_flow_call_api': 'calc_flow%dD(host ndarray window) -> host ndarrays (pinned), rank 0' % ndim,
+               'calc_flow_call_plain_numpy_value': call_rate_pageable}
 
     if rank != 0:
         return
@@ -541,7 +553,7 @@ def main():
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'fp32'])
     ap.add_argument('--timepoints', type=int, default=None, help='limit the number of output timepoints (debug)')
     ap.add_argument('--generic', action='store_true', help='force the generic kernels')
-    ap.add_argument('--e2e-timepoints', type=int, default=6)
+    ap.add_argument('--e2e-timepoints', type=int, default=12)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-stage-events', action='store_true', help='do not bracket the launches with CUDA events')
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -228,7 +228,7 @@ class FlowStream:
         else:
             if self.stage_ev[k] is not None:
                 self.stage_ev[k].synchronize()             # pinned staging buffer is free again
-            self.stage[k][...] = a                         # host copy (and dtype conversion) into pinned memory
+            _lib.parallel_copy(self.stage[k], a)           # host copy (and dtype conversion) into pinned memory
             src = self.stage[k]
         with torch.cuda.stream(self.s_in):
             if self.ring_free_ev is not None:

@@ -171,3 +171,29 @@ def test_stage_times_cover_every_launch():
         assert set(ctx.stage_times()) == {'temporal', 'generic'}
     finally:
         ctx.set_profile(False)
+
+
+def test_plain_numpy_call_uses_pooled_pinned_memory():
+    """calc_flow3D(pageable ndarray) stages its window through pinned memory and returns arrays in pooled pinned blocks;
+    a dead result's block is handed out again; strided / byte-swapped / unsupported-dtype inputs convert on the way."""
+    import gc
+    from opticalflow3d_dev_b200 import _lib, calc_flow3D
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 3000, (9, 6, 40, 64)).astype(np.uint16)
+    ref = calc_flow3D(img, 1, 1, 2)
+    assert all(_lib.is_pinned(r) for r in ref) and not _lib.is_pinned(img)
+    keep = [r.copy() for r in ref]
+    del ref
+    gc.collect()
+    blocks = len(_lib._RANGES)
+    again = calc_flow3D(img, 1, 1, 2)
+    assert len(_lib._RANGES) == blocks                         # staging and results came back from the pool
+    assert all(np.array_equal(a, b) for a, b in zip(again, keep))
+    # same values through a strided view, a byte-swapped copy and an int8-free unsupported dtype (uint64 -> float64)
+    wide = np.zeros((9, 6, 40, 128), np.uint16); wide[..., ::2] = img
+    assert all(np.array_equal(a, b) for a, b in zip(calc_flow3D(wide[..., ::2], 1, 1, 2), keep))
+    assert all(np.array_equal(a, b) for a, b in zip(calc_flow3D(img.astype('>u2'), 1, 1, 2), keep))
+    assert all(np.array_equal(a, b) for a, b in zip(calc_flow3D(img.astype(np.uint64), 1, 1, 2), keep))
+    # a longer stack: only the centre window is staged
+    long = np.concatenate([img[:1]] * 2 + [img] + [img[-1:]] * 2)
+    assert all(np.array_equal(a, b) for a, b in zip(calc_flow3D(long, 1, 1, 2), keep))
