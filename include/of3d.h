@@ -134,6 +134,18 @@ OF3D_API int of3d_flow_frames(of3d_ctx* ctx, int ndim, const void* const* frames
                      void* vx, void* vy, void* vz, void* rel, int out_mem);
 
 /*
+ * The synchronous host-to-host call (calc_flow3D(ndarray) -> ndarrays), pipelined: of3d_window_upload copies frame k of
+ * n_frames from page-locked host memory into a device-resident window on a dedicated copy stream and returns at once, so
+ * that the caller can prepare (stage, convert) frame k + 1 while frame k crosses PCIe; frames are uploaded in order
+ * 0..n_frames-1.  of3d_window_flow waits for the uploads on the device and runs the operator of of3d_flow_frames on the
+ * window.  Replaces the np.double(images) conversion + filtering of calc_flow.py:225-357 / 67-168 for host arrays.
+ */
+OF3D_API int of3d_window_upload(of3d_ctx* ctx, int k, int n_frames, const void* host_frame, size_t frame_bytes);
+OF3D_API int of3d_window_flow(of3d_ctx* ctx, int ndim, int in_dtype, int64_t nz, int64_t ny, int64_t nx,
+                              const of3d_taps* taps, int precision, unsigned flags,
+                              void* vx, void* vy, void* vz, void* rel, int out_mem);
+
+/*
  * The operator in two stages, for volumes sharded by z-slab across GPUs.  The temporal
  * derivative (calc_flow.py:276-278) is local in z, the spatial stages are not: a rank runs stage 1 on the planes
  * it owns, exchanges R + Rw halo planes of (ic, dt0) with its neighbours (NCCL), runs stage 2 on the extended slab

@@ -48,6 +48,8 @@ SIGNATURES = {
     'of3d_launch_count': (_i64, [_vp]),
     'of3d_host_alloc': (_i, [C.POINTER(_vp), _sz]),
     'of3d_host_free': (_i, [_vp]),
+    'of3d_window_upload': (_i, [_vp, _i, _i, _vp, _sz]),
+    'of3d_window_flow': (_i, [_vp, _i, _i, _i64, _i64, _i64, C.POINTER(Taps), _i, _u, _vp, _vp, _vp, _vp, _i]),
     'of3d_set_profile': (_i, [_vp, _i]),
     'of3d_stage_times': (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
     'of3d_stage_name': (C.c_char_p, [_i]),
@@ -239,19 +241,44 @@ def pinned_pool_trim():
 _COPY_POOL = None
 
 
-def parallel_copy(dst, src, min_bytes=8 << 20):
-    """dst[...] = src with several threads (NumPy releases the GIL inside copyto): one thread moves ~10 GB/s, which is
-    less than PCIe.  Both arrays are split along their first axis."""
+def _copy_pool():
     global _COPY_POOL
-    if src.nbytes < min_bytes or dst.shape[0] < 2:
-        np.copyto(dst, src, casting='unsafe')
-        return
     if _COPY_POOL is None:
         from concurrent.futures import ThreadPoolExecutor
         _COPY_POOL = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
+    return _COPY_POOL
+
+
+def parallel_copy_frames(dst, src, on_frame, parts=4):
+    """dst[k] = src[k] for every frame k with several threads, calling on_frame(k) (in order) as soon as frame k is
+    complete.  All pieces are queued at once, frame-major, so the workers never idle between frames (a fork-join per
+    frame runs at a third of the rate) and the caller can ship frame k while the later ones are still being copied."""
+    pool = _copy_pool()
+    groups = []
+    for k in range(dst.shape[0]):
+        n = dst.shape[1] if dst.ndim > 1 else 1
+        p = max(1, min(parts, n))
+        if dst.ndim < 2 or p == 1:
+            groups.append([pool.submit(np.copyto, dst[k:k + 1], src[k:k + 1], 'unsafe')])
+        else:
+            e = [n * i // p for i in range(p + 1)]
+            groups.append([pool.submit(np.copyto, dst[k, a:b], src[k, a:b], 'unsafe') for a, b in zip(e[:-1], e[1:]) if b > a])
+    for k, g in enumerate(groups):
+        for f in g:
+            f.result()
+        on_frame(k)
+
+
+def parallel_copy(dst, src, min_bytes=8 << 20):
+    """dst[...] = src with several threads (NumPy releases the GIL inside copyto): one thread moves ~10 GB/s, which is
+    less than PCIe.  Both arrays are split along their first axis."""
+    if src.nbytes < min_bytes or dst.shape[0] < 2:
+        np.copyto(dst, src, casting='unsafe')
+        return
+    pool = _copy_pool()
     n = dst.shape[0]
-    parts = min(n, _COPY_POOL._max_workers * 2)
+    parts = min(n, pool._max_workers)
     edges = [n * i // parts for i in range(parts + 1)]
-    futs = [_COPY_POOL.submit(np.copyto, dst[a:b], src[a:b], 'unsafe') for a, b in zip(edges[:-1], edges[1:]) if b > a]
+    futs = [pool.submit(np.copyto, dst[a:b], src[a:b], 'unsafe') for a, b in zip(edges[:-1], edges[1:]) if b > a]
     for f in futs:
         f.result()

@@ -69,22 +69,38 @@ def _device_dtype(dt):
     raise TypeError('calc_flow: unsupported image dtype %s' % dt)
 
 
-def _host_frames(images, first, kt):
-    """The kt frames images[first:first+kt] as one C-contiguous array of a supported dtype in PAGE-LOCKED memory.
-    Arrays that already are (e.g. allocated with _lib.pinned_empty) pass through; anything else is copied -- converting
-    dtype / byte order / strides on the way -- into a pooled pinned block by several threads: the driver's own staging of
-    pageable memory moves a 1.9 GB window at a fifth of the PCIe rate."""
+def _upload_window(ctx, images, first, kt):
+    """Upload the kt frames images[first:first+kt] into the library's device-resident window and return their dtype.
+    Every frame must cross PCIe from PAGE-LOCKED memory: the driver's own staging of pageable memory moves a 1.9 GB
+    window at a fifth of the PCIe rate.  Frames that already are pinned (e.g. _lib.pinned_empty), C-contiguous and of a
+    supported dtype go straight; anything else is copied -- converting dtype / byte order / strides on the way -- into a
+    pooled pinned block by several threads, frame by frame, while the previous frame is still in flight
+    (of3d_window_upload returns at once)."""
     a = np.asarray(images)
     dt = _device_dtype(a.dtype)
     win = a[first:first + kt]
-    if win.dtype == dt and win.flags.c_contiguous and _lib.is_pinned(win):
-        return win
-    try:
-        stage = _lib.pinned_empty(win.shape, dt, pooled=True)
-    except RuntimeError:                                     # page-locking failed: let the driver stage pageable memory
-        return np.ascontiguousarray(win, dtype=dt)
-    _lib.parallel_copy(stage, win)
-    return stage
+    direct = win.dtype == dt and all(win[k].flags.c_contiguous for k in range(kt)) and _lib.is_pinned(win)
+    stage = None
+    if not direct:
+        try:
+            stage = _lib.pinned_empty(win.shape, dt, pooled=True)
+        except RuntimeError:                                 # page-locking failed: let the driver stage pageable memory
+            win, direct = np.ascontiguousarray(win, dtype=dt), True
+    src = win if direct else stage
+
+    def ship(k):
+        _lib.check(ctx.lib.of3d_window_upload(ctx.handle, k, kt, C.c_void_p(src[k].ctypes.data), src[k].nbytes), 'of3d_window_upload')
+
+    if direct:
+        for k in range(kt):
+            ship(k)
+    elif win.nbytes < (8 << 20):
+        np.copyto(stage, win, casting='unsafe')
+        for k in range(kt):
+            ship(k)
+    else:
+        _lib.parallel_copy_frames(stage, win, ship)
+    return dt, src                                           # keep the source alive until the flow call has synchronised
 
 
 def _host_outputs(sp, dtypes):
@@ -135,7 +151,7 @@ def _run(images, spatialSig, tSig, wSig, ndim, precision, device, exact, generic
         ctx = _lib.get_context(_default_device() if device is None else device)
         kt = keep[3].size
         first = (nt + 1) // 2 - 1 - kt // 2                 # first frame the t-filter of the centre frame touches
-        a = _host_frames(images, first, kt)
+        in_dt, alive = _upload_window(ctx, images, first, kt)
         odt = np.float64 if precision == 'fp64' else np.float32
         odts = [odt] * (nout - 1) + [np.float32 if rel_f32 else odt]
         if out is None:
@@ -147,13 +163,11 @@ def _run(images, spatialSig, tSig, wSig, ndim, precision, device, exact, generic
                 raise ValueError('out must be %d C-contiguous %s arrays of shape %s (the reliability may be float32)'
                                  % (nout, np.dtype(odt).name, sp))
         ptrs = [C.c_void_p(o.ctypes.data) for o in outs]
-        fptr = (C.c_void_p * kt)(*[a[k].ctypes.data for k in range(kt)])
         o4 = ptrs if ndim == 3 else [ptrs[0], ptrs[1], None, ptrs[2]]
-        rc = ctx.lib.of3d_flow_frames(ctx.handle, ndim, fptr, _lib.DTYPE_CODES[a.dtype], _lib.HOST,
-                                      sp[0] if ndim == 3 else 1, sp[-2], sp[-1], C.byref(taps), prec, flags,
-                                      o4[0], o4[1], o4[2], o4[3], _lib.HOST)
-        _lib.check(rc, 'of3d_flow_frames')
-        del keep
+        rc = ctx.lib.of3d_window_flow(ctx.handle, ndim, _lib.DTYPE_CODES[in_dt], sp[0] if ndim == 3 else 1, sp[-2], sp[-1],
+                                      C.byref(taps), prec, flags, o4[0], o4[1], o4[2], o4[3], _lib.HOST)
+        _lib.check(rc, 'of3d_window_flow')
+        del keep, alive
         return outs
 
     lib = ctx.lib

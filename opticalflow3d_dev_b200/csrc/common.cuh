@@ -60,6 +60,12 @@ struct of3d_ctx {
     int async = 0;
     int64_t launches = 0;
     int sm_count = 148;
+    // device-resident input window fed frame by frame (of3d_window_upload / of3d_window_flow)
+    cudaStream_t s_up = nullptr;
+    cudaEvent_t ev_up = nullptr;
+    char* win = nullptr;
+    size_t win_cap = 0, win_frame = 0;
+    int win_n = 0;
     // optional per-stage device timing (of3d_set_profile): every launch is bracketed by events on `stream`
     int profile = 0;
     std::vector<cudaEvent_t> ev_pool;                 // recycled events

@@ -436,6 +436,9 @@ OF3D_API int of3d_destroy(of3d_ctx* c) {
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->ws) cudaFree(c->ws);
+    if (c->win) cudaFree(c->win);
+    if (c->s_up) cudaStreamDestroy(c->s_up);
+    if (c->ev_up) cudaEventDestroy(c->ev_up);
     delete c;
     return OF3D_OK;
 }
@@ -466,6 +469,49 @@ OF3D_API int of3d_flow_frames(of3d_ctx* ctx, int ndim, const void* const* frames
                      int64_t nx, const of3d_taps* taps, int precision, unsigned flags, void* vx, void* vy, void* vz, void* rel,
                      int out_mem) {
     return flow_frames_impl(ctx, ndim, frames, in_dtype, in_mem, nz, ny, nx, taps, precision, flags, vx, vy, vz, rel, out_mem);
+}
+
+OF3D_API int of3d_window_upload(of3d_ctx* c, int k, int n_frames, const void* host_frame, size_t frame_bytes) {
+    if (!c || !host_frame || n_frames < 1 || n_frames > kMaxFrames || k < 0 || k >= n_frames || frame_bytes == 0) { set_error("bad argument"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->s_up) {
+        OF3D_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+        OF3D_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+    }
+    const size_t slot = align_up(frame_bytes);
+    if (c->win_cap < slot * n_frames) {
+        OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        OF3D_CUDA_TRY(cudaStreamSynchronize(c->s_up));
+        if (c->win) cudaFree(c->win);
+        c->win = nullptr; c->win_cap = 0;
+        cudaError_t e = cudaMalloc(&c->win, slot * n_frames);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("device window allocation of " + std::to_string(slot * n_frames) + " bytes failed: out of memory"); return OF3D_ERR_NOMEM; }
+        c->win_cap = slot * n_frames;
+    }
+    if (k == 0) {
+        // the previous window may still be read by kernels of an asynchronous call
+        OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->win_frame = frame_bytes; c->win_n = n_frames;
+    } else if (frame_bytes != c->win_frame || n_frames != c->win_n) { set_error("window frames must be uploaded in order 0..n-1 with one size"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaMemcpyAsync(c->win + (size_t)k * slot, host_frame, frame_bytes, cudaMemcpyHostToDevice, c->s_up));
+    OF3D_CUDA_TRY(cudaEventRecord(c->ev_up, c->s_up));
+    return OF3D_OK;
+}
+
+OF3D_API int of3d_window_flow(of3d_ctx* c, int ndim, int in_dtype, int64_t nz, int64_t ny, int64_t nx, const of3d_taps* taps, int precision,
+                              unsigned flags, void* vx, void* vy, void* vz, void* rel, int out_mem) {
+    if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
+    if (int rc = check_taps(taps)) return rc;
+    if (!c->win || c->win_n != taps->nT || c->win_frame != (size_t)(nz * ny * nx) * dtype_size(in_dtype)) {
+        set_error("of3d_window_flow: the uploaded window does not match (frames or frame size)");
+        return OF3D_ERR_ARG;
+    }
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    OF3D_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_up, 0));
+    const void* frames[kMaxFrames];
+    const size_t slot = align_up(c->win_frame);
+    for (int k = 0; k < taps->nT; ++k) frames[k] = c->win + (size_t)k * slot;
+    return flow_frames_impl(c, ndim, frames, in_dtype, OF3D_DEVICE, nz, ny, nx, taps, precision, flags, vx, vy, vz, rel, out_mem);
 }
 
 OF3D_API int of3d_temporal(of3d_ctx* ctx, int ndim, const void* const* frames, int in_dtype, int in_mem, int64_t nz, int64_t ny,
