@@ -26,3 +26,23 @@ def test_percentile_plan_large_float32_index_quantisation():
     lo, hi, g = percentile_plan(n, 90, np.float32)
     part = np.partition(a, [lo, hi])
     assert lerp(part[lo], part[hi], g) == np.percentile(a, 90)
+
+
+def test_threaded_host_copies():
+    """_lib.parallel_copy / parallel_copy_frames (staging of pageable windows): values, dtype conversion, strides, order"""
+    from opticalflow3d_dev_b200 import _lib
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 60000, (5, 16, 96, 130)).astype(np.uint16)
+    b = np.empty(a.shape, np.float64)
+    seen = []
+    _lib.parallel_copy_frames(b, a, seen.append)
+    assert seen == [0, 1, 2, 3, 4] and np.array_equal(b, a)
+    c = np.empty((5, 16, 96, 65), np.uint16)
+    _lib.parallel_copy_frames(c, a[..., ::2].astype('>u2'), lambda k: None)      # strided + byte-swapped source
+    assert np.array_equal(c, a[..., ::2])
+    d = np.empty_like(a)
+    _lib.parallel_copy(d, a, min_bytes=1)
+    assert np.array_equal(d, a)
+    one = np.empty(7)
+    _lib.parallel_copy_frames(one, np.arange(7.), lambda k: None)
+    assert np.array_equal(one, np.arange(7.))

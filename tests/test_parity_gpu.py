@@ -347,19 +347,22 @@ def test_rel_f32_flag_is_one_rounding_of_the_float64_value():
     assert t32[3].dtype == torch.float32 and np.array_equal(t32[3].cpu().numpy(), r32[3])
 
 
+@pytest.mark.parametrize('shape', [(7, 21, 50, 200), (7, 3, 20, 64), (7, 1, 16, 68), (7, 9, 12, 36)])
 @pytest.mark.parametrize('precision', ['fp64', 'fp32'])
-def test_tma_window_march_equals_cp_async_march(precision, monkeypatch):
+def test_tma_window_march_equals_cp_async_march(precision, shape, monkeypatch):
     """The TMA-fed window z march (tensor-map tiles, padded gradient volumes) and the cp.async march it replaces do the
     same arithmetic in the same order: bit-identical results.  Columns: one full 64-column block, one partial group."""
     from opticalflow3d_dev_b200.synth import make_stack
-    img = make_stack((7, 21, 50, 200), seed=99, dtype=np.uint16)
+    img = make_stack(shape, seed=99, dtype=np.uint16)
     cf = _cf()
     monkeypatch.delenv('OF3D_NO_TMA', raising=False)
+    monkeypatch.setenv('OF3D_FORCE_TMA', '1')                  # small volumes default to the cp.async march
     a = cf.calc_flow3D(img, 3, 1, 4, precision=precision, rel_dtype='float64')
+    monkeypatch.delenv('OF3D_FORCE_TMA')
     monkeypatch.setenv('OF3D_NO_TMA', '1')
     b = cf.calc_flow3D(img, 3, 1, 4, precision=precision, rel_dtype='float64')
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
-    if precision == 'fp64':
+    if precision == 'fp64' and shape[1] > 8:
         ref = orc.lk_flow3d(img, 3, 1, 4, rel_mode='float64')
         assert_flow_close(a[:3], ref[:3], ref[3], 1e-9, 'tma')
