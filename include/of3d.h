@@ -134,13 +134,20 @@ OF3D_API int of3d_flow_frames(of3d_ctx* ctx, int ndim, const void* const* frames
                      void* vx, void* vy, void* vz, void* rel, int out_mem);
 
 /*
- * The synchronous host-to-host call (calc_flow3D(ndarray) -> ndarrays), pipelined: of3d_window_upload copies frame k of
- * n_frames from page-locked host memory into a device-resident window on a dedicated copy stream and returns at once, so
- * that the caller can prepare (stage, convert) frame k + 1 while frame k crosses PCIe; frames are uploaded in order
- * 0..n_frames-1.  of3d_window_flow waits for the uploads on the device and runs the operator of of3d_flow_frames on the
- * window.  Replaces the np.double(images) conversion + filtering of calc_flow.py:225-357 / 67-168 for host arrays.
+ * The synchronous host-to-host call (calc_flow3D(ndarray) -> ndarrays), pipelined.  of3d_window_upload copies `bytes`
+ * bytes at byte `offset` of frame k (of n_frames, frame_bytes each) from page-locked host memory into a device-resident
+ * window on a dedicated copy stream and returns at once, so that the caller can prepare (stage, convert) the next piece
+ * while this one crosses PCIe.  A window starts with (k = 0, offset = 0); pieces may come in any order after that.
+ * of3d_window_flow runs the operator of of3d_flow_frames on the window.  For large 3D volumes returned to the host it
+ * works in z slabs of of3d_window_slab(...) planes: a slab is computed (on its extension by the operator's z support,
+ * bit-identical to the whole-volume run) as soon as the planes it needs have arrived -- ship the pieces z-chunk by
+ * z-chunk, every frame's chunk before the next chunk -- and copied back while the next slab computes.
+ * of3d_window_slab returns 0 when the call is not pipelined.  Replaces the np.double(images) conversion + filtering of
+ * calc_flow.py:225-357 / 67-168 for host arrays.
  */
-OF3D_API int of3d_window_upload(of3d_ctx* ctx, int k, int n_frames, const void* host_frame, size_t frame_bytes);
+OF3D_API int64_t of3d_window_slab(int ndim, int64_t nz, int64_t ny, int64_t nx, const of3d_taps* taps);
+OF3D_API int of3d_window_upload(of3d_ctx* ctx, int k, int n_frames, const void* host_src, size_t frame_bytes, size_t offset,
+                                size_t bytes);
 OF3D_API int of3d_window_flow(of3d_ctx* ctx, int ndim, int in_dtype, int64_t nz, int64_t ny, int64_t nx,
                               const of3d_taps* taps, int precision, unsigned flags,
                               void* vx, void* vy, void* vz, void* rel, int out_mem);

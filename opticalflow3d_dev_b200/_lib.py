@@ -48,7 +48,8 @@ SIGNATURES = {
     'of3d_launch_count': (_i64, [_vp]),
     'of3d_host_alloc': (_i, [C.POINTER(_vp), _sz]),
     'of3d_host_free': (_i, [_vp]),
-    'of3d_window_upload': (_i, [_vp, _i, _i, _vp, _sz]),
+    'of3d_window_slab': (_i64, [_i, _i64, _i64, _i64, C.POINTER(Taps)]),
+    'of3d_window_upload': (_i, [_vp, _i, _i, _vp, _sz, _sz, _sz]),
     'of3d_window_flow': (_i, [_vp, _i, _i, _i64, _i64, _i64, C.POINTER(Taps), _i, _u, _vp, _vp, _vp, _vp, _i]),
     'of3d_set_profile': (_i, [_vp, _i]),
     'of3d_stage_times': (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
@@ -267,6 +268,16 @@ def parallel_copy_frames(dst, src, on_frame, parts=4):
         for f in g:
             f.result()
         on_frame(k)
+
+
+def parallel_copy_pieces(pieces, on_piece):
+    """np.copyto(dst, src) for every (dst, src) of `pieces` with several threads, all queued at once; on_piece(i) is
+    called in order as soon as piece i is complete (the later ones are still being copied)."""
+    pool = _copy_pool()
+    futs = [pool.submit(np.copyto, d, s_, 'unsafe') for d, s_ in pieces]
+    for i, f in enumerate(futs):
+        f.result()
+        on_piece(i)
 
 
 def parallel_copy(dst, src, min_bytes=8 << 20):

@@ -69,13 +69,14 @@ def _device_dtype(dt):
     raise TypeError('calc_flow: unsupported image dtype %s' % dt)
 
 
-def _upload_window(ctx, images, first, kt):
+def _upload_window(ctx, images, first, kt, chunk=0):
     """Upload the kt frames images[first:first+kt] into the library's device-resident window and return their dtype.
-    Every frame must cross PCIe from PAGE-LOCKED memory: the driver's own staging of pageable memory moves a 1.9 GB
+    Every piece must cross PCIe from PAGE-LOCKED memory: the driver's own staging of pageable memory moves a 1.9 GB
     window at a fifth of the PCIe rate.  Frames that already are pinned (e.g. _lib.pinned_empty), C-contiguous and of a
     supported dtype go straight; anything else is copied -- converting dtype / byte order / strides on the way -- into a
-    pooled pinned block by several threads, frame by frame, while the previous frame is still in flight
-    (of3d_window_upload returns at once)."""
+    pooled pinned block by several threads while earlier pieces are in flight (of3d_window_upload returns at once).
+    chunk > 0 (3D): pieces are z-chunks of `chunk` planes shipped chunk-major -- every frame's chunk before the next
+    chunk -- which is the order the library's z-slab pipeline consumes them in; otherwise whole frames."""
     a = np.asarray(images)
     dt = _device_dtype(a.dtype)
     win = a[first:first + kt]
@@ -87,19 +88,27 @@ def _upload_window(ctx, images, first, kt):
         except RuntimeError:                                 # page-locking failed: let the driver stage pageable memory
             win, direct = np.ascontiguousarray(win, dtype=dt), True
     src = win if direct else stage
-
-    def ship(k):
-        _lib.check(ctx.lib.of3d_window_upload(ctx.handle, k, kt, C.c_void_p(src[k].ctypes.data), src[k].nbytes), 'of3d_window_upload')
-
-    if direct:
-        for k in range(kt):
-            ship(k)
-    elif win.nbytes < (8 << 20):
-        np.copyto(stage, win, casting='unsafe')
-        for k in range(kt):
-            ship(k)
+    nz = win.shape[1]
+    fbytes = src[0].nbytes
+    pbytes = fbytes // nz if nz else 0                       # bytes of one z plane (first spatial axis)
+    if chunk > 0 and win.ndim == 4:
+        cuts = [(z0, min(nz, z0 + chunk)) for z0 in range(0, nz, chunk)]
     else:
-        _lib.parallel_copy_frames(stage, win, ship)
+        cuts = [(0, nz)]
+    pieces = [(k, z0, z1) for (z0, z1) in cuts for k in range(kt)]
+
+    def ship(i):
+        k, z0, z1 = pieces[i]
+        _lib.check(ctx.lib.of3d_window_upload(ctx.handle, k, kt, C.c_void_p(src[k].ctypes.data + z0 * pbytes), fbytes,
+                                              z0 * pbytes, (z1 - z0) * pbytes), 'of3d_window_upload')
+
+    if direct or win.nbytes < (8 << 20):
+        if not direct:
+            np.copyto(stage, win, casting='unsafe')
+        for i in range(len(pieces)):
+            ship(i)
+    else:
+        _lib.parallel_copy_pieces([(stage[k, z0:z1], win[k, z0:z1]) for k, z0, z1 in pieces], ship)
     return dt, src                                           # keep the source alive until the flow call has synchronised
 
 
@@ -151,7 +160,8 @@ def _run(images, spatialSig, tSig, wSig, ndim, precision, device, exact, generic
         ctx = _lib.get_context(_default_device() if device is None else device)
         kt = keep[3].size
         first = (nt + 1) // 2 - 1 - kt // 2                 # first frame the t-filter of the centre frame touches
-        in_dt, alive = _upload_window(ctx, images, first, kt)
+        slab = int(ctx.lib.of3d_window_slab(ndim, sp[0] if ndim == 3 else 1, sp[-2], sp[-1], C.byref(taps)))
+        in_dt, alive = _upload_window(ctx, images, first, kt, chunk=slab)
         odt = np.float64 if precision == 'fp64' else np.float32
         odts = [odt] * (nout - 1) + [np.float32 if rel_f32 else odt]
         if out is None:

@@ -61,11 +61,17 @@ struct of3d_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     // device-resident input window fed frame by frame (of3d_window_upload / of3d_window_flow)
-    cudaStream_t s_up = nullptr;
+    cudaStream_t s_up = nullptr, s_dn = nullptr;
     cudaEvent_t ev_up = nullptr;
-    char* win = nullptr;
+    char* win = nullptr;                                // [win_n frames][slot]
     size_t win_cap = 0, win_frame = 0;
     int win_n = 0;
+    struct Part { size_t off; cudaEvent_t ev; };       // uploaded pieces in shipping order (byte offset in a frame)
+    std::vector<Part> parts;
+    std::vector<cudaEvent_t> part_pool;
+    char* pipe = nullptr;                               // ic, dt0 and two sets of slab outputs of the pipelined host call
+    size_t pipe_cap = 0;
+    cudaEvent_t ev_c = nullptr, ev_dn[2] = {nullptr, nullptr};
     // optional per-stage device timing (of3d_set_profile): every launch is bracketed by events on `stream`
     int profile = 0;
     std::vector<cudaEvent_t> ev_pool;                 // recycled events

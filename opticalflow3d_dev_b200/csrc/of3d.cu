@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -437,8 +438,14 @@ OF3D_API int of3d_destroy(of3d_ctx* c) {
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->ws) cudaFree(c->ws);
     if (c->win) cudaFree(c->win);
+    if (c->pipe) cudaFree(c->pipe);
     if (c->s_up) cudaStreamDestroy(c->s_up);
+    if (c->s_dn) cudaStreamDestroy(c->s_dn);
     if (c->ev_up) cudaEventDestroy(c->ev_up);
+    if (c->ev_c) cudaEventDestroy(c->ev_c);
+    for (auto e : c->ev_dn) if (e) cudaEventDestroy(e);
+    for (auto& pt : c->parts) cudaEventDestroy(pt.ev);
+    for (auto e : c->part_pool) cudaEventDestroy(e);
     delete c;
     return OF3D_OK;
 }
@@ -471,30 +478,118 @@ OF3D_API int of3d_flow_frames(of3d_ctx* ctx, int ndim, const void* const* frames
     return flow_frames_impl(ctx, ndim, frames, in_dtype, in_mem, nz, ny, nx, taps, precision, flags, vx, vy, vz, rel, out_mem);
 }
 
-OF3D_API int of3d_window_upload(of3d_ctx* c, int k, int n_frames, const void* host_frame, size_t frame_bytes) {
-    if (!c || !host_frame || n_frames < 1 || n_frames > kMaxFrames || k < 0 || k >= n_frames || frame_bytes == 0) { set_error("bad argument"); return OF3D_ERR_ARG; }
+OF3D_API int64_t of3d_window_slab(int ndim, int64_t nz, int64_t ny, int64_t nx, const of3d_taps* t) {
+    if (ndim != 3 || !t || getenv("OF3D_NO_SLAB_PIPELINE")) return 0;
+    const int64_t H = std::max(std::max(t->nD, t->nG), t->nS) / 2 + t->nW / 2;
+    const int64_t slab = 16;
+    // worth it when the copies dominate (>= 32 Mvoxel) and the extension (slab + 2H) stays well below the volume
+    if ((nz * ny * nx < (int64_t(32) << 20) && !getenv("OF3D_FORCE_SLAB_PIPELINE")) || nz < 4 * slab || nz < 4 * H) return 0;
+    return slab;
+}
+
+OF3D_API int of3d_window_upload(of3d_ctx* c, int k, int n_frames, const void* host_src, size_t frame_bytes, size_t offset, size_t bytes) {
+    if (!c || !host_src || n_frames < 1 || n_frames > kMaxFrames || k < 0 || k >= n_frames || frame_bytes == 0 || bytes == 0 ||
+        offset + bytes > frame_bytes) { set_error("bad argument"); return OF3D_ERR_ARG; }
     OF3D_CUDA_TRY(cudaSetDevice(c->device));
     if (!c->s_up) {
         OF3D_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+        OF3D_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_dn, cudaStreamNonBlocking));
         OF3D_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+        OF3D_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_c, cudaEventDisableTiming));
+        for (auto& e : c->ev_dn) OF3D_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     const size_t slot = align_up(frame_bytes);
-    if (c->win_cap < slot * n_frames) {
-        OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
-        OF3D_CUDA_TRY(cudaStreamSynchronize(c->s_up));
-        if (c->win) cudaFree(c->win);
-        c->win = nullptr; c->win_cap = 0;
-        cudaError_t e = cudaMalloc(&c->win, slot * n_frames);
-        if (e != cudaSuccess) { cudaGetLastError(); set_error("device window allocation of " + std::to_string(slot * n_frames) + " bytes failed: out of memory"); return OF3D_ERR_NOMEM; }
-        c->win_cap = slot * n_frames;
-    }
-    if (k == 0) {
+    const bool first = k == 0 && offset == 0;
+    if (first) {
         // the previous window may still be read by kernels of an asynchronous call
         OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        OF3D_CUDA_TRY(cudaStreamSynchronize(c->s_up));
+        if (c->win_cap < slot * n_frames) {
+            if (c->win) cudaFree(c->win);
+            c->win = nullptr; c->win_cap = 0;
+            cudaError_t e = cudaMalloc(&c->win, slot * n_frames);
+            if (e != cudaSuccess) { cudaGetLastError(); set_error("device window allocation of " + std::to_string(slot * n_frames) + " bytes failed: out of memory"); return OF3D_ERR_NOMEM; }
+            c->win_cap = slot * n_frames;
+        }
         c->win_frame = frame_bytes; c->win_n = n_frames;
-    } else if (frame_bytes != c->win_frame || n_frames != c->win_n) { set_error("window frames must be uploaded in order 0..n-1 with one size"); return OF3D_ERR_ARG; }
-    OF3D_CUDA_TRY(cudaMemcpyAsync(c->win + (size_t)k * slot, host_frame, frame_bytes, cudaMemcpyHostToDevice, c->s_up));
+        for (auto& pt : c->parts) c->part_pool.push_back(pt.ev);
+        c->parts.clear();
+    } else if (frame_bytes != c->win_frame || n_frames != c->win_n) { set_error("a window starts with frame 0, offset 0 and keeps one frame size"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaMemcpyAsync(c->win + (size_t)k * slot + offset, host_src, bytes, cudaMemcpyHostToDevice, c->s_up));
+    cudaEvent_t ev = nullptr;
+    if (!c->part_pool.empty()) { ev = c->part_pool.back(); c->part_pool.pop_back(); }
+    else OF3D_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    OF3D_CUDA_TRY(cudaEventRecord(ev, c->s_up));
+    c->parts.push_back({offset, ev});
     OF3D_CUDA_TRY(cudaEventRecord(c->ev_up, c->s_up));
+    return OF3D_OK;
+}
+
+// The synchronous host call in z slabs: while slab s is copied back, slab s + 1 is computed and the planes of later
+// slabs are still arriving.  A slab is computed on its extension by H = R_gradient + R_window planes (the z support of
+// the operator), of which only the interior is returned: bit-identical to the whole-volume run.
+static int window_flow_pipelined(of3d_ctx* c, int in_dtype, int64_t nz, int64_t ny, int64_t nx, const of3d_taps* t, int precision,
+                                 unsigned flags, void* const hout[4], int64_t slab) {
+    const int64_t plane = ny * nx, n = nz * plane;
+    const size_t ts = precision == OF3D_FP32 ? 4 : 8, ib = dtype_size(in_dtype);
+    const int64_t H = std::max(std::max(t->nD, t->nG), t->nS) / 2 + t->nW / 2;
+    const int64_t ext_max = std::min(nz, slab + 2 * H);
+    const size_t osz[4] = {ts, ts, ts, (precision == OF3D_FP64 && (flags & OF3D_FLAG_REL_F32)) ? (size_t)4 : ts};
+    // device buffers: ic, dt0, two sets of four extended-slab outputs
+    const size_t vol_b = align_up((size_t)n * ts), ext_b = align_up((size_t)ext_max * plane * 8);
+    const size_t need = 2 * vol_b + 8 * ext_b;
+    if (c->pipe_cap < need) {
+        OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        OF3D_CUDA_TRY(cudaStreamSynchronize(c->s_dn));
+        if (c->pipe) cudaFree(c->pipe);
+        c->pipe = nullptr; c->pipe_cap = 0;
+        cudaError_t e = cudaMalloc(&c->pipe, need);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("device allocation of " + std::to_string(need) + " bytes failed: out of memory"); return OF3D_ERR_NOMEM; }
+        c->pipe_cap = need;
+    }
+    // one arena size for every stage call of the pipeline (no re-allocation in flight)
+    if (int rc = ws_ensure(c, plan_bytes(3, 0, ext_max * plane, plane, in_dtype, precision, OF3D_DEVICE, OF3D_DEVICE))) return rc;
+    char* ic = c->pipe; char* dt0 = c->pipe + vol_b;
+    char* ext[2][4];
+    for (int q = 0; q < 2; ++q) for (int i = 0; i < 4; ++i) ext[q][i] = c->pipe + 2 * vol_b + (size_t)(q * 4 + i) * ext_b;
+    const size_t slot = align_up(c->win_frame);
+    const int saved_async = c->async;
+    c->async = 1;                                               // the stage calls below must not synchronise
+    int rc = OF3D_OK;
+    int64_t tz = 0;                                             // planes whose temporal stage has been enqueued
+    int ns = 0;
+    for (int64_t a = 0; a < nz && rc == OF3D_OK; a += slab, ++ns) {
+        const int64_t b = std::min(nz, a + slab), a2 = std::max<int64_t>(0, a - H), b2 = std::min(nz, b + H);
+        if (tz < b2) {
+            // wait (on the device) for every uploaded piece that holds planes below b2
+            const size_t limit = (size_t)b2 * plane * ib;
+            cudaEvent_t ev = nullptr;
+            for (const auto& pt : c->parts) if (pt.off < limit) ev = pt.ev;
+            if (ev) OF3D_CUDA_TRY(cudaStreamWaitEvent(c->stream, ev, 0));
+            const void* frames[kMaxFrames];
+            for (int k = 0; k < t->nT; ++k) frames[k] = c->win + (size_t)k * slot + (size_t)tz * plane * ib;
+            rc = flow_staged(c, 1, 3, frames, in_dtype, OF3D_DEVICE, b2 - tz, ny, nx, t, precision, flags, ic + (size_t)tz * plane * ts,
+                             dt0 + (size_t)tz * plane * ts, nullptr, nullptr, nullptr, nullptr, OF3D_DEVICE);
+            if (rc) break;
+            tz = b2;
+        }
+        const int q = ns & 1;
+        if (ns >= 2) OF3D_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_dn[q], 0));   // the copy-back of slab ns - 2 has left the buffers
+        rc = flow_staged(c, 2, 3, nullptr, in_dtype, OF3D_DEVICE, b2 - a2, ny, nx, t, precision, flags, ic + (size_t)a2 * plane * ts,
+                         dt0 + (size_t)a2 * plane * ts, ext[q][0], ext[q][1], ext[q][2], ext[q][3], OF3D_DEVICE);
+        if (rc) break;
+        OF3D_CUDA_TRY(cudaEventRecord(c->ev_c, c->stream));
+        OF3D_CUDA_TRY(cudaStreamWaitEvent(c->s_dn, c->ev_c, 0));
+        for (int i = 0; i < 4; ++i)
+            OF3D_CUDA_TRY(cudaMemcpyAsync((char*)hout[i] + (size_t)a * plane * osz[i], ext[q][i] + (size_t)(a - a2) * plane * osz[i],
+                                          (size_t)(b - a) * plane * osz[i], cudaMemcpyDeviceToHost, c->s_dn));
+        OF3D_CUDA_TRY(cudaEventRecord(c->ev_dn[q], c->s_dn));
+    }
+    c->async = saved_async;
+    cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->s_dn);
+    if (rc) return rc;
+    OF3D_CUDA_TRY(e1);
+    OF3D_CUDA_TRY(e2);
     return OF3D_OK;
 }
 
@@ -506,7 +601,14 @@ OF3D_API int of3d_window_flow(of3d_ctx* c, int ndim, int in_dtype, int64_t nz, i
         set_error("of3d_window_flow: the uploaded window does not match (frames or frame size)");
         return OF3D_ERR_ARG;
     }
+    if (precision != OF3D_FP64 && precision != OF3D_FP32) { set_error("precision must be OF3D_FP64 or OF3D_FP32"); return OF3D_ERR_ARG; }
     OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    // large 3D volumes going back to the host: z-slab pipeline (upload, compute and copy-back overlap)
+    const int64_t slab = of3d_window_slab(ndim, nz, ny, nx, taps);
+    if (out_mem == OF3D_HOST && slab > 0 && vx && vy && vz && rel) {
+        void* hout[4] = {vx, vy, vz, rel};
+        return window_flow_pipelined(c, in_dtype, nz, ny, nx, taps, precision, flags, hout, slab);
+    }
     OF3D_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_up, 0));
     const void* frames[kMaxFrames];
     const size_t slot = align_up(c->win_frame);

@@ -366,3 +366,30 @@ def test_tma_window_march_equals_cp_async_march(precision, shape, monkeypatch):
     if precision == 'fp64' and shape[1] > 8:
         ref = orc.lk_flow3d(img, 3, 1, 4, rel_mode='float64')
         assert_flow_close(a[:3], ref[:3], ref[3], 1e-9, 'tma')
+
+
+@pytest.mark.parametrize('shape,sig,precision', [
+    ((7, 90, 40, 64), (3, 1, 4), 'fp64'),          # nz >= 4 * (R + R_w) = 84: six slabs of 16 planes, the last one short
+    ((7, 97, 33, 50), (3, 1, 4), 'fp64'),          # odd sizes (cp.async march), ragged last slab
+    ((9, 70, 36, 40), (1, 1, 2), 'fp32'),          # short support: H = 9
+])
+def test_z_slab_pipelined_host_call_is_bit_identical(shape, sig, precision, monkeypatch):
+    """of3d_window_flow in z slabs (upload / compute / copy-back overlapped, pieces shipped chunk-major) returns exactly
+    what the whole-volume call returns, for pageable and for pinned inputs."""
+    from opticalflow3d_dev_b200 import _lib
+    from opticalflow3d_dev_b200.synth import make_stack
+    img = make_stack(shape, seed=7, dtype=np.uint16)
+    cf = _cf()
+    monkeypatch.setenv('OF3D_NO_SLAB_PIPELINE', '1')
+    ref = cf.calc_flow3D(img, *sig, precision=precision)
+    monkeypatch.delenv('OF3D_NO_SLAB_PIPELINE')
+    monkeypatch.setenv('OF3D_FORCE_SLAB_PIPELINE', '1')
+    ctx = _lib.get_context(0)
+    taps, keep = _lib.make_taps(__import__('opticalflow3d_dev_b200.taps', fromlist=['flow_taps']).flow_taps(*sig))
+    import ctypes as C
+    assert ctx.lib.of3d_window_slab(3, shape[1], shape[2], shape[3], C.byref(taps)) == 16
+    got = cf.calc_flow3D(img, *sig, precision=precision)
+    pin = _lib.pinned_empty(img.shape, img.dtype); pin[...] = img
+    got2 = cf.calc_flow3D(pin, *sig, precision=precision)
+    for r, a, b in zip(ref, got, got2):
+        assert a.dtype == r.dtype and np.array_equal(a, r) and np.array_equal(b, r)
