@@ -156,18 +156,36 @@ class TiffPage:
         o = self.offsets
         return all(o[i] + self.bytecounts[i] == o[i + 1] for i in range(len(o) - 1))
 
-    def asarray(self, fh):
+    def runs(self):
+        """(file offset, byte count) of the strips, adjacent strips merged"""
+        nbytes = self.shape[0] * self.shape[1] * self.dtype.itemsize
+        out, pos = [], 0
+        for off, cnt in zip(self.offsets, self.bytecounts):
+            cnt = min(cnt, nbytes - pos)
+            if cnt <= 0:
+                break
+            if out and out[-1][0] + out[-1][1] == off:
+                out[-1][1] += cnt
+            else:
+                out.append([off, cnt])
+            pos += cnt
+        return out
+
+    def readinto(self, fh, dst):
+        """Read the page straight into `dst`, a writable C-contiguous array of the page's shape and (file) dtype."""
         if self.compression != 1:
             raise NotImplementedError('tiffio: compressed TIFF (Compression=%d) is not supported' % self.compression)
-        n = self.shape[0] * self.shape[1]
-        buf = bytearray(n * self.dtype.itemsize)
+        mv = memoryview(dst).cast('B')
         pos = 0
-        for off, cnt in zip(self.offsets, self.bytecounts):
+        for off, cnt in self.runs():
             fh.seek(off)
-            cnt = min(cnt, len(buf) - pos)
-            fh.readinto(memoryview(buf)[pos:pos + cnt])
+            if fh.readinto(mv[pos:pos + cnt]) != cnt:
+                raise ValueError('tiffio: truncated image data')
             pos += cnt
-        a = np.frombuffer(buf, dtype=self.dtype, count=n).reshape(self.shape)
+
+    def asarray(self, fh):
+        a = np.empty(self.shape, dtype=self.dtype)
+        self.readinto(fh, a)
         return a.astype(self.dtype.newbyteorder('=')) if not self.dtype.isnative else a
 
 
@@ -263,17 +281,33 @@ class TiffFile:
         n = len(self.pages)
         return n, ((n,) if n > 1 else ()) + p0.shape
 
-    def asarray(self):
+    def asarray(self, out=None):
+        """The whole series.  out: a C-contiguous array of the series' shape and native dtype (e.g. page-locked memory)
+        to read into -- every plane goes from the file straight to its place, no intermediate copy."""
         n, shape = self.series_shape()
         p0 = self.pages[0]
-        with open(self.path, 'rb') as fh:
+        native = p0.dtype.newbyteorder('=')
+        if out is not None:
+            if out.size != int(np.prod(shape)) or out.dtype != native or not out.flags.c_contiguous:
+                raise ValueError('tiffio: out must be a C-contiguous %s array of %s elements' % (native, tuple(shape)))
+            a = out.reshape(shape)
+        else:
+            a = np.empty(shape, dtype=native)
+        raw = a                          # file bytes land in place; a foreign byte order is swapped at the end
+        with open(self.path, 'rb', buffering=0) as fh:
             if n > len(self.pages):      # ImageJ > 4 GB convention: one IFD, all planes contiguous after it
                 fh.seek(p0.offsets[0])
-                a = np.fromfile(fh, dtype=p0.dtype, count=int(np.prod(shape)))
+                if fh.readinto(memoryview(raw.reshape(-1)).cast('B')) != raw.nbytes:
+                    raise ValueError('tiffio: truncated image data')
             else:
-                a = np.stack([p.asarray(fh) for p in self.pages[:n]]) if n > 1 else p0.asarray(fh)
-        a = a.reshape(shape)
-        return a.astype(a.dtype.newbyteorder('=')) if not a.dtype.isnative else a
+                planes = raw.reshape((n,) + p0.shape)
+                for i, p in enumerate(self.pages[:n]):
+                    if p.shape != p0.shape or p.dtype != p0.dtype:
+                        raise ValueError('tiffio: pages of different shape or dtype in one series')
+                    p.readinto(fh, planes[i])
+        if not p0.dtype.isnative:
+            a.byteswap(inplace=True)
+        return a if out is None else out
 
     def close(self):
         pass
@@ -285,8 +319,8 @@ class TiffFile:
         return False
 
 
-def imread(path):
-    return TiffFile(path).asarray()
+def imread(path, out=None):
+    return TiffFile(path).asarray(out=out)
 
 
 def memmap(path, mode='r'):

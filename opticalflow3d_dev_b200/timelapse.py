@@ -56,6 +56,21 @@ class _FrameSource:
         self.Nt, self.Nz, self.ndim = Nt, Nz, spatialDimensions
         self.stack = tiffio.memmap(imDir / fileList[0]) if fileType == 'OneTif' else None
 
+    def frame_into(self, t, out):
+        """Read frame t straight into `out` (page-locked staging of the frame's shape and dtype); False if the file's
+        layout does not allow it (the caller then takes frame(t))."""
+        if self.stack is not None:
+            a = self.stack[t]
+            if a.shape != out.shape:
+                return False
+            _lib.parallel_copy(out, a)
+            return True
+        try:
+            tiffio.imread(self.imDir / self.files[t], out=out)
+            return True
+        except ValueError:
+            return False
+
     def frame(self, t):
         if self.stack is not None:
             a = self.stack[t]
@@ -214,6 +229,14 @@ class FlowStream:
         self.pending = None
         return centre, tuple(self.h_out[hslot])
 
+    def staging(self):
+        """The page-locked staging array the NEXT push may be given (filled by the caller, e.g. read from a file
+        straight into it): push(eng.staging(), pinned=True) uploads it without any host copy."""
+        k = self.t % 2
+        if self.stage_ev[k] is not None:
+            self.stage_ev[k].synchronize()                 # its previous upload has left the buffer
+        return self.stage[k]
+
     def push(self, frame, pinned=False):
         """Feed the next frame (host array).  pinned=True: `frame` already lives in page-locked memory (e.g.
         _lib.pinned_empty), has the stream's dtype, is C-contiguous and stays untouched until the next push -- it is
@@ -296,35 +319,46 @@ def _stream(imDir, fileList, fileType, ndim, dims, sig, NtChunk, NtSlice, starts
     names = ['vx', 'vy', 'vz', 'rel'] if ndim == 3 else ['vx', 'vy', 'rel']
     t_start = {}
 
-    def write_all(arrs, centre):
-        tstr = str(centre).zfill(4)
-        for nm, a in zip(names, arrs):
-            out = a
-            if ndim == 3 and nm == 'rel':
-                out = a.astype(np.float32, copy=False) # dtype the reference writes (calc_flow.py:355-357, :529)
-            tiffio.imwrite(str(savedir / name) + '_' + nm + '_t' + tstr + '.tiff', out, photometric='minisblack')
-        if verbose:
-            print(str(datetime.now()) + ' - Frame ' + str(centre) + ' saved.  Duration: ' + str(datetime.now() - t_start[centre]))
+    def write_one(nm, a, centre):
+        out = a
+        if ndim == 3 and nm == 'rel':
+            out = a.astype(np.float32, copy=False)     # dtype the reference writes (calc_flow.py:355-357, :529)
+        tiffio.imwrite(str(savedir / name) + '_' + nm + '_t' + str(centre).zfill(4) + '.tiff', out, photometric='minisblack')
+
+    def write_all(pool, arrs, centre):
+        """one task per output file; returns a waiter for the whole timepoint"""
+        fs = [pool.submit(write_one, nm, a, centre) for nm, a in zip(names, arrs)]
+
+        def wait():
+            for f in fs:
+                f.result()
+            if verbose:
+                print(str(datetime.now()) + ' - Frame ' + str(centre) + ' saved.  Duration: ' + str(datetime.now() - t_start[centre]))
+        return wait
 
     # frames needed by this rank: window starts hh in `starts` touch frames hh+off .. hh+off+kt-1
     t_lo, t_hi = starts[0] + off, starts[-1] + off + kt
     from collections import deque
-    with ThreadPoolExecutor(max_workers=max(1, min(int(writers), 2))) as pool:
-        futs = deque()                                     # writers in flight; a result stays valid for two more pushes
+    with ThreadPoolExecutor(max_workers=max(1, int(writers))) as pool:
+        futs = deque()                                     # timepoints being written; a result stays valid for one more push
         for t in range(t_lo, t_hi):
             while len(futs) > 1:
-                futs.popleft().result()
+                futs.popleft()()
             centre_next = t - (kt - 1) + kt // 2           # centre of the window this frame completes
             if t - t_lo >= kt - 1:
                 t_start[centre_next] = datetime.now()
                 if verbose:
                     print(str(datetime.now()) + ' - Processing frame ' + str(centre_next) + '...')
-            done = eng.push(src.frame(t).astype(in_dt, copy=False))
+            buf = eng.staging()
+            if src.frame_into(t, buf):                     # file -> page-locked staging, no intermediate copy
+                done = eng.push(buf, pinned=True)
+            else:
+                done = eng.push(src.frame(t).astype(in_dt, copy=False))
             if done is not None:
-                futs.append(pool.submit(write_all, done[1], done[0]))
+                futs.append(write_all(pool, done[1], done[0]))
         done = eng.flush()
         if done is not None:
-            futs.append(pool.submit(write_all, done[1], done[0]))
+            futs.append(write_all(pool, done[1], done[0]))
         for f in futs:
-            f.result()
+            f()
     eng.close()
