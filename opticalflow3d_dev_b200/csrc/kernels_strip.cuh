@@ -239,7 +239,7 @@ template <int NCH, int NHALF>
 __device__ __forceinline__ int solve_unit(int warp, int ui) {
     const int q = warp >> 2, sm = warp & 3;            // q-th warp of scheduler sm
     if (NCH == 9 && NHALF == 2) {                      // 18 warps (5,5,4,4), 16 units: 3,3,5,5 (one unit per warp --
-                                                       // 4,4,4,4 -- measured 15 % slower: the 5-warp schedulers bind)
+                                                       // 4,4,4,4 -- measured 15 % slower, 2,2,6,6 4 % slower)
         if (sm >= 2) return ui == 0 ? (sm - 2) * 5 + q : ((ui == 1 && q == 0) ? (sm - 2) * 5 + 4 : -1);
         return (ui == 0 && q < 3) ? 10 + sm * 3 + q : -1;
     } else if (NCH == 9 && NHALF == 1) {               // 9 warps (3,2,2,2), 8 units: 0,3,3,2
