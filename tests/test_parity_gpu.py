@@ -393,3 +393,32 @@ def test_z_slab_pipelined_host_call_is_bit_identical(shape, sig, precision, monk
     got2 = cf.calc_flow3D(pin, *sig, precision=precision)
     for r, a, b in zip(ref, got, got2):
         assert a.dtype == r.dtype and np.array_equal(a, r) and np.array_equal(b, r)
+
+
+def test_window_abi_rejects_mismatched_calls():
+    """of3d_window_upload / of3d_window_flow argument checking (no silent garbage): a window starts with frame 0 at
+    offset 0, keeps one frame size, and the flow call must match what was uploaded."""
+    import ctypes as C
+    from opticalflow3d_dev_b200 import _lib
+    from opticalflow3d_dev_b200.taps import flow_taps
+    ctx = _lib.get_context(0)
+    lib, h = ctx.lib, ctx.handle
+    taps, keep = _lib.make_taps(flow_taps(1, 1, 2))
+    kt = keep[3].size
+    sp = (6, 20, 24)
+    fr = _lib.pinned_empty((kt,) + sp, np.uint16); fr[...] = 7
+    fb = fr[0].nbytes
+    out = [_lib.pinned_empty(sp, np.float64) for _ in range(4)]
+    ptr = lambda a: C.c_void_p(a.ctypes.data)
+    assert lib.of3d_window_upload(h, 0, kt, ptr(fr[0]), fb, 0, fb) == _lib.OK
+    assert lib.of3d_window_upload(h, 1, kt, ptr(fr[1]), fb // 2, 0, fb // 2) != _lib.OK          # other frame size
+    assert lib.of3d_window_upload(h, 1, kt, ptr(fr[1]), fb, fb // 2, fb) != _lib.OK              # beyond the frame
+    assert lib.of3d_window_upload(h, kt, kt, ptr(fr[1]), fb, 0, fb) != _lib.OK                   # frame index
+    for k in range(1, kt):
+        assert lib.of3d_window_upload(h, k, kt, ptr(fr[k]), fb, 0, fb) == _lib.OK
+    args = (C.byref(taps), _lib.FP64, 0, ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), _lib.HOST)
+    assert lib.of3d_window_flow(h, 3, _lib.U16, sp[0], sp[1], sp[2] + 1, *args) != _lib.OK       # other shape
+    assert 'does not match' in _lib.last_error()
+    assert lib.of3d_window_flow(h, 3, _lib.U16, *sp, *args) == _lib.OK
+    assert np.abs(out[0]).max() < 1e-9 and np.all(np.isfinite(out[3]))                          # constant image: no flow
+    assert lib.of3d_window_slab(2, 1, 4096, 4096, C.byref(taps)) == 0                            # 2D is never slabbed
