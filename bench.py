@@ -455,6 +455,11 @@ def gpu_arm(args, rank, world, local_rank):
             h2d, d2h = eng.h2d_bytes - b0, eng.d2h_bytes - b1
             eng.close()
             del eng
+        if world > 1:
+            dist.barrier()                                       # the other ranks' streams are done: rank 0 measures alone
+        if n_e2e and rank == 0:
+            import gc
+            gc.collect()
             # the synchronous per-window call, for comparison
             hout = tuple(_lib.pinned_empty(tuple(sp), np.float32 if (ndim == 3 and i == 3) else np_odt) for i in range(ndim + 1))
             fn = calc_flow3D if ndim == 3 else calc_flow2D
@@ -470,8 +475,10 @@ def gpu_arm(args, rank, world, local_rank):
             tc = time.perf_counter()
             r_ = fn(pg[1:1 + kt], *sig, **kw2)
             call_rate_pageable = vol / (time.perf_counter() - tc)
-            del r_, pg
-        else:
+            del r_, pg, hout
+            gc.collect()
+            _lib.pinned_pool_trim()
+        if not n_e2e:
             h2d = d2h = 0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         nn = torch.tensor([float(n_e2e), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
