@@ -255,6 +255,46 @@ __device__ __forceinline__ int solve_unit(int warp, int ui) {
     }
 }
 
+// Solve the 32 voxels of unit `unit` of batch b (row v / TX, column v % TX of the parked batch) and store the results.
+// Solve the voxels of NU units of batch b at once (row v / TX, column v % TX of the parked batch; NU independent
+// dependency chains per lane) and store the results.
+template <typename T, int NCH, int TX, int R, int NU = 1>
+__device__ __forceinline__ void solve_unit_voxels(const T* park, int parkrow, int b, int unit, int lane, int cs0, int nout, int n_c,
+                                                  int64_t plane_off, int64_t stride_m, int m0, T* vx, T* vy, T* vz, T* rel) {
+    constexpr int RB = kStripRB;
+    bool ok[NU];
+    const T* qv[NU];
+    int64_t idx[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        const int v = (unit + u) * 32 + lane;
+        const int s_i = v / TX, s_col = v % TX;
+        const int s_c = cs0 + s_col;
+        const int j = b * RB - 2 * R + s_i;
+        ok[u] = j >= 0 && j < nout && s_c < n_c;
+        const int prow = ((j % RB) + RB) % RB;
+        qv[u] = park + ((b & 1) * RB + prow) * parkrow + s_col;
+        idx[u] = plane_off + (int64_t)(m0 + j) * stride_m + s_c;
+    }
+    if (NCH == 9) {
+        Flow3 rr[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u)           // parked values of masked voxels are finite garbage at worst: solved, not stored
+            rr[u] = solve3<false>((double)qv[u][0], (double)qv[u][TX], (double)qv[u][2 * TX], (double)qv[u][3 * TX], (double)qv[u][4 * TX],
+                                  (double)qv[u][5 * TX], (double)qv[u][6 * TX], (double)qv[u][7 * TX], (double)qv[u][8 * TX]);
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+            if (ok[u]) { vx[idx[u]] = (T)rr[u].vx; vy[idx[u]] = (T)rr[u].vy; vz[idx[u]] = (T)rr[u].vz; rel[idx[u]] = (T)rr[u].rel; }
+    } else {
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            if (!ok[u]) continue;
+            const Flow2 rr = solve2<false>((double)qv[u][0], (double)qv[u][TX], (double)qv[u][2 * TX], (double)qv[u][3 * TX], (double)qv[u][4 * TX]);
+            vx[idx[u]] = (T)rr.vx; vy[idx[u]] = (T)rr.vy; rel[idx[u]] = (T)rr.rel;
+        }
+    }
+}
+
 template <typename T, int K, int P, int NCH, int NHALF, bool PROD>
 __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const StripArgs<T, K> a) {
     constexpr int RB = kStripRB, R = K / 2, TX = 32 * NHALF;
@@ -322,25 +362,8 @@ __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const 
             for (int ui = 0; ui < 4; ++ui) {
                 const int unit = solve_unit<NCH, NHALF>(warp, ui);
                 if (unit < 0) break;
-                const int v = unit * 32 + lane;                               // voxel of the batch: row v / TX, column v % TX
-                const int s_i = v / TX, s_col = v % TX;
-                const int s_c = cs0 + s_col;
-                const int j = b * RB - 2 * R + s_i;
-                if (j >= 0 && j < nout && s_c < g.n_c) {
-                    const int prow = ((j % RB) + RB) % RB;
-                    const T* qv = park + ((b & 1) * RB + prow) * PARKROW + s_col;
-                    const int64_t idx = (int64_t)o * g.stride_o + (int64_t)(m0 + j) * g.stride_m + s_c;
-                    if (NCH == 9) {
-                        const Flow3 rr = solve3<false>((double)qv[0], (double)qv[TX], (double)qv[2 * TX], (double)qv[3 * TX],
-                                                       (double)qv[4 * TX], (double)qv[5 * TX], (double)qv[6 * TX],
-                                                       (double)qv[7 * TX], (double)qv[8 * TX]);
-                        a.vx[idx] = (T)rr.vx; a.vy[idx] = (T)rr.vy; a.vz[idx] = (T)rr.vz; a.rel[idx] = (T)rr.rel;
-                    } else {
-                        const Flow2 rr = solve2<false>((double)qv[0], (double)qv[TX], (double)qv[2 * TX], (double)qv[3 * TX],
-                                                       (double)qv[4 * TX]);
-                        a.vx[idx] = (T)rr.vx; a.vy[idx] = (T)rr.vy; a.rel[idx] = (T)rr.rel;
-                    }
-                }
+                solve_unit_voxels<T, NCH, TX, R>(park, PARKROW, b, unit, lane, cs0, nout, g.n_c, (int64_t)o * g.stride_o, g.stride_m, m0,
+                                                 a.vx, a.vy, a.vz, a.rel);
             }
         }
     }
