@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(double* out, int iters,
             if (i < NI) asm volatile("add.s32 %0, %0, %1;" : "+r"(q[i & 3]) : "r"(q[(i + 1) & 3]));
             if (i + 24 < NI) asm volatile("add.s32 %0, %0, %1;" : "+r"(q[(i + 2) & 3]) : "r"(q[(i + 3) & 3]));
             if (i < NL) { double t; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "l"(sp + 32 * i + (q[0] & 0)) ); l += t * 0; }
+            if (i < -NL) { double t, t2; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t), "=d"(t2) : "l"(sh + 2 * (threadIdx.x & 31) + 64 * i + (q[0] & 0)) ); l += (t + t2) * 0; }
         }
     }
     double s = l + q[0] + q[1] + q[2] + q[3];
@@ -56,5 +57,7 @@ int main() {
     run<0, 2, 16>(sms, it); run<0, 4, 16>(sms, it); run<16, 2, 16>(sms, it);
     run<0, 0, 20>(sms, it); run<16, 2, 20>(sms, it); run<24, 2, 20>(sms, it);
     run<0, 0, 8>(sms, it); run<16, 2, 8>(sms, it);
+    // negative NL: that many 128-bit shared loads (two doubles per lane) instead of 64-bit ones
+    run<0, -1, 16>(sms, it); run<0, -2, 16>(sms, it); run<0, -4, 16>(sms, it); run<16, -2, 16>(sms, it);
     return 0;
 }
