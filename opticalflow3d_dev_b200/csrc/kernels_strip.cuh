@@ -15,6 +15,7 @@
 // strip_window_solve  window x pass + y pass + per-voxel solve (calc_flow.py:300-357 / 133-168): the NCH window
 //                     sums of a voxel only ever exist in registers and shared memory.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "kernels_march.cuh"
 #include "solve.cuh"
@@ -114,6 +115,108 @@ struct StripStage {
     }
 };
 
+// Row-major variant of the staging for 8-byte elements (fp64): rows are fetched with 16-byte cp.async (two elements per
+// lane and instruction, half the LDGSTS of the element-wise stage -- the gradient strips ran at 72-78 % L1/LSU
+// utilisation) and gathered with 128-bit shared loads.  Lane (row l & 7, block l >> 3) makes the eight lanes of a
+// quarter-warp read eight different rows; a row stride = 2 (mod 4) elements puts them on eight different 16-byte bank
+// groups.  Chunks lie on the even-column grid (the volume's row length must be even and its base 16-byte aligned), so a
+// chunk is either entirely inside the row or entirely outside: outside chunks are fetched from the clamped chunk and the
+// edge strips then overwrite their out-of-range columns with the edge value (scipy's mode='nearest').
+template <typename T, int KG>
+struct StripStage16 {
+    static_assert(sizeof(T) == 8, "16-byte staging is written for 8-byte elements");
+    static constexpr int R = KG / 2, AL = R & 1;                   // AL: extra leading column -> even first column
+    static constexpr int ROWLEN = (32 + KG - 1 + AL + 1) / 2 * 2;  // elements fetched per row
+    static constexpr int NCHUNK = ROWLEN / 2;
+    static constexpr int ROWSTRIDE = ROWLEN + ((ROWLEN % 4 == 2) ? 0 : 2);
+    static constexpr int BUF = kStripRB * ROWSTRIDE;
+    static constexpr int elems = 2 * BUF + kStripRB * kXwRow;       // two batches in flight + the gathered rows
+    T* rows;                // [2][RB][ROWSTRIDE]; batch b lives in buffer b & 1
+    T* xw;                  // [RB][kXwRow]
+    uint32_t rows_s;
+    const T* src;           // plane base of the input
+    int col0;               // first (even) column of the staged rows: cw0 - R - AL
+    int n_c, nmm1, mfirst;
+    int64_t stride_m;
+
+    __device__ __forceinline__ void init(T* smem_warp, int cw0, int m_first, const StripGeom& g) {
+        rows = smem_warp;
+        xw = smem_warp + 2 * BUF;
+        rows_s = (uint32_t)__cvta_generic_to_shared(rows);
+        col0 = cw0 - R - AL;
+        n_c = g.n_c; nmm1 = g.n_m - 1; mfirst = m_first; stride_m = g.stride_m;
+    }
+    // lane (row = lane / 4, q = lane % 4) fetches chunks q, q + 4, ... of its row
+    __device__ __forceinline__ void issue(int b) {
+        const int lane = threadIdx.x & 31, r = lane >> 2, q = lane & 3;
+        const int m = max(0, min(mfirst + b * kStripRB + r, nmm1));
+        const T* row = src + (int64_t)m * stride_m;
+        const uint32_t dst = rows_s + (uint32_t)(((b & 1) * BUF + r * ROWSTRIDE + 2 * q) * sizeof(T));
+#pragma unroll
+        for (int i = 0; i < (NCHUNK + 3) / 4; ++i) {
+            if (NCHUNK % 4 == 0 || q + 4 * i < NCHUNK) {
+                const int c = max(0, min(col0 + 2 * (q + 4 * i), n_c - 2));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(8 * i * sizeof(T))), "l"(row + c) : "memory");
+            }
+        }
+        cp_async_commit();
+    }
+    // edge strips: columns outside [0, n_c) take the edge value
+    __device__ __forceinline__ void fix_edges(int b) {
+        if (col0 >= 0 && col0 + ROWLEN <= n_c) return;
+        const int lane = threadIdx.x & 31, r = lane >> 2, q = lane & 3;
+        T* row = rows + (b & 1) * BUF + r * ROWSTRIDE;
+        if (col0 < 0) {
+            const T v = row[-col0];
+            for (int e = q; e < -col0; e += 4) row[e] = v;
+        }
+        const int last = n_c - 1 - col0;                            // element index of the last valid column
+        if (last < ROWLEN - 1) {
+            const T v = row[max(last, 0)];
+            for (int e = last + 1 + q; e < ROWLEN; e += 4) row[e] = v;
+        }
+        __syncwarp();
+    }
+    // gather with filter f (KF <= KG taps, centred in the staged halo), result to xw
+    // (SYM = +1 / -1: only the first half of the (anti)symmetric taps is read, cf. ring_push)
+    template <int KF, int SYM>
+    __device__ __forceinline__ void gather(const Taps<T, KF>& f, int b) {
+        constexpr int XB = kStripXB, OFF = AL + (KG - KF) / 2;      // element of tap 0 of output 0 of block 0
+        constexpr int EB = OFF & ~1, SKIP = OFF & 1;                // pairs start at the even element EB
+        constexpr int NPAIR = (SKIP + XB + KF - 1 + 1) / 2;
+        const int lane = threadIdx.x & 31, g_r = lane & 7, g_b = lane >> 3;
+        const double2* s0 = reinterpret_cast<const double2*>(rows + (b & 1) * BUF + g_r * ROWSTRIDE + EB + g_b * XB);
+        T ga[XB];
+#pragma unroll
+        for (int i = 0; i < XB; ++i) ga[i] = T(0);
+#pragma unroll
+        for (int p = 0; p < NPAIR; ++p) {
+            const double2 v2 = s0[p];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int mm = 2 * p + h - SKIP;                    // input element relative to tap 0 of output 0
+                const T v = h ? v2.y : v2.x;
+                const T vn = SYM < 0 ? -v : v;
+#pragma unroll
+                for (int i = 0; i < XB; ++i) {
+                    const int k = mm - i;
+                    if (mm >= 0 && k >= 0 && k < KF) {
+                        const bool mirror = k > KF / 2;
+                        ga[i] = fma(f.w[mirror ? KF - 1 - k : k], mirror ? vn : v, ga[i]);
+                    }
+                }
+            }
+        }
+        T* d = xw + g_r * kXwRow + g_b * (XB + 1);
+#pragma unroll
+        for (int i = 0; i < XB; ++i) d[i] = ga[i];
+    }
+    __device__ __forceinline__ T gathered(int r) const {
+        const int lane = threadIdx.x & 31;
+        return xw[r * kXwRow + lane + lane / 8];
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // Gradient stage.  Roles (one warp each, independent):
 //   0  in dt0: gather G_x, march G_y                      -> out0            (dt before the z pass / dt in 2D)
@@ -128,18 +231,21 @@ struct GradStripArgs {
     T* out[4];              // out[3] == nullptr in 2D
 };
 
-template <typename T, int KR>
-constexpr size_t grad_strip_smem(int wpb) { return (size_t)wpb * StripStage<T, KR, 1, 2>::elems * sizeof(T); }
+template <typename T, int KR, bool V16 = false>
+constexpr size_t grad_strip_smem(int wpb) {
+    if constexpr (V16) return (size_t)wpb * StripStage16<T, KR>::elems * sizeof(T);
+    else return (size_t)wpb * StripStage<T, KR, 1, 2>::elems * sizeof(T);
+}
 
 // One role.  Each role is its own kernel instantiation: dispatched inside one kernel the three bodies get a merged
 // register allocation of 228 registers (8 warps per SM); separately they need 56-95.
-template <typename T, int KR, int KS, int P, int ROLE>
+template <typename T, int KR, int KS, int P, int ROLE, bool V16>
 __device__ __forceinline__ void strip_grad_body(const GradStripArgs<T, KR, KS>& a, T* smem_warp, int strip, int chunk, int o) {
     constexpr int RB = kStripRB, R = KR / 2, RS = KS / 2;
     constexpr int KGATHER = ROLE == 1 ? KS : KR;            // taps of the x filter
     constexpr int KA = ROLE == 2 ? KS : KR;                 // taps of the (first) y filter
     constexpr int lagA = R + KA / 2;                        // the stream with radius rf completes row m0 + s - R - rf
-    using Stage = StripStage<T, KR, 1, 2>;
+    using Stage = typename std::conditional<V16, StripStage16<T, KR>, StripStage<T, KR, 1, 2>>::type;
     const StripGeom& g = a.g;
     const int lane = threadIdx.x & 31;
     const int cw0 = strip * 32;
@@ -150,7 +256,8 @@ __device__ __forceinline__ void strip_grad_body(const GradStripArgs<T, KR, KS>& 
 
     Stage st;
     st.init(smem_warp, cw0, m0 - R, g);
-    st.src[0] = (ROLE == 0 ? a.dt0 : a.ic) + (int64_t)o * g.stride_o;
+    if constexpr (V16) st.src = (ROLE == 0 ? a.dt0 : a.ic) + (int64_t)o * g.stride_o;
+    else st.src[0] = (ROLE == 0 ? a.dt0 : a.ic) + (int64_t)o * g.stride_o;
     const int64_t obase = (int64_t)o * g.stride_o + cw0 + lane;
     T* const oA = a.out[ROLE == 0 ? 0 : (ROLE == 1 ? 1 : 2)] + obase;
     T* const oB = (ROLE == 1 && a.out[3]) ? a.out[3] + obase : nullptr;   // second stream of role 1: S_y (3D only)
@@ -171,9 +278,16 @@ __device__ __forceinline__ void strip_grad_body(const GradStripArgs<T, KR, KS>& 
         for (int bi = 0; bi < P / RB; ++bi, ++b) {
             cp_async_wait<1>();                                               // batch b has landed, b + 1 is in flight
             __syncwarp();
-            if (ROLE == 0) st.template gather<KR, false>(a.fG, 0, b);
-            else if (ROLE == 1) st.template gather<KS, false>(a.fS, 0, b);
-            else st.template gather<KR, false>(a.fD, 0, b);
+            if constexpr (V16) {
+                st.fix_edges(b);
+                if (ROLE == 0) st.template gather<KR, 1>(a.fG, b);
+                else if (ROLE == 1) st.template gather<KS, 1>(a.fS, b);
+                else st.template gather<KR, -1>(a.fD, b);
+            } else {
+                if (ROLE == 0) st.template gather<KR, false>(a.fG, 0, b);
+                else if (ROLE == 1) st.template gather<KS, false>(a.fS, 0, b);
+                else st.template gather<KR, false>(a.fD, 0, b);
+            }
             __syncwarp();
             st.issue(b + 2);                                                  // into the buffer just consumed
 #pragma unroll
@@ -197,7 +311,7 @@ __device__ __forceinline__ void strip_grad_body(const GradStripArgs<T, KR, KS>& 
     cp_async_wait<0>();
 }
 
-template <typename T, int KR, int KS, int P, int ROLE, int WPB>
+template <typename T, int KR, int KS, int P, int ROLE, int WPB, bool V16 = false>
 __global__ void __launch_bounds__(WPB * 32) strip_grad(const GradStripArgs<T, KR, KS> a) {
     static_assert(P >= KR && KR >= KS && P % kStripRB == 0, "bad unroll period");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -209,7 +323,8 @@ __global__ void __launch_bounds__(WPB * 32) strip_grad(const GradStripArgs<T, KR
     const int strip = (int)(task % nstrips); task /= nstrips;
     const int chunk = (int)(task % g.n_chunks);
     const int o = (int)(task / g.n_chunks);
-    strip_grad_body<T, KR, KS, P, ROLE>(a, reinterpret_cast<T*>(smem_raw) + warp * StripStage<T, KR, 1, 2>::elems, strip, chunk, o);
+    constexpr int kElems = V16 ? StripStage16<typename std::conditional<V16, T, double>::type, KR>::elems : StripStage<T, KR, 1, 2>::elems;
+    strip_grad_body<T, KR, KS, P, ROLE, V16>(a, reinterpret_cast<T*>(smem_raw) + warp * kElems, strip, chunk, o);
 }
 
 // ------------------------------------------------------------------------------------------------
