@@ -16,7 +16,6 @@ fallback: without libof3d.so or without a CUDA device every call raises.
 from __future__ import annotations
 
 import ctypes as C
-import math
 import os
 import sys
 

@@ -63,3 +63,25 @@ def test_process_flow_argument_errors(tmp_path):
         process_flow(tmp_path, 'x_t.*', fileType='Other')
     with pytest.raises(SystemExit, match='more than one file was found'):
         process_flow(tmp_path, 'x_t.*', fileType='OneTif')
+
+
+def test_imread_into_preallocated_buffer(tmp_path):
+    """imread(out=) reads every plane straight into the caller's (e.g. page-locked) array; shape may differ as long as
+    the element count matches; dtype and contiguity are checked."""
+    import numpy as np
+    import pytest
+    from opticalflow3d_dev_b200 import tiffio
+    a = (np.arange(5 * 6 * 7).reshape(5, 6, 7) * 13 % 4001).astype(np.uint16)
+    p = tmp_path / 'stack.tif'
+    tiffio.imwrite(p, a)
+    out = np.zeros((5, 6, 7), np.uint16)
+    assert tiffio.imread(p, out=out) is out and np.array_equal(out, a)
+    flat = np.zeros(5 * 6 * 7, np.uint16)
+    tiffio.imread(p, out=flat)
+    assert np.array_equal(flat.reshape(a.shape), a)
+    with pytest.raises(ValueError):
+        tiffio.imread(p, out=np.zeros((5, 6, 7), np.float32))
+    with pytest.raises(ValueError):
+        tiffio.imread(p, out=np.zeros((5, 6, 8), np.uint16))
+    with pytest.raises(ValueError):
+        tiffio.imread(p, out=np.zeros((5, 6, 14), np.uint16)[..., ::2])
