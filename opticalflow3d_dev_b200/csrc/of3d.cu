@@ -555,36 +555,40 @@ static int window_flow_pipelined(of3d_ctx* c, int in_dtype, int64_t nz, int64_t 
     const size_t slot = align_up(c->win_frame);
     const int saved_async = c->async;
     c->async = 1;                                               // the stage calls below must not synchronise
-    int rc = OF3D_OK;
-    int64_t tz = 0;                                             // planes whose temporal stage has been enqueued
-    int ns = 0;
-    for (int64_t a = 0; a < nz && rc == OF3D_OK; a += slab, ++ns) {
-        const int64_t b = std::min(nz, a + slab), a2 = std::max<int64_t>(0, a - H), b2 = std::min(nz, b + H);
-        if (tz < b2) {
-            // wait (on the device) for every uploaded piece that holds planes below b2
-            const size_t limit = (size_t)b2 * plane * ib;
-            cudaEvent_t ev = nullptr;
-            for (const auto& pt : c->parts) if (pt.off < limit) ev = pt.ev;
-            if (ev) OF3D_CUDA_TRY(cudaStreamWaitEvent(c->stream, ev, 0));
-            const void* frames[kMaxFrames];
-            for (int k = 0; k < t->nT; ++k) frames[k] = c->win + (size_t)k * slot + (size_t)tz * plane * ib;
-            rc = flow_staged(c, 1, 3, frames, in_dtype, OF3D_DEVICE, b2 - tz, ny, nx, t, precision, flags, ic + (size_t)tz * plane * ts,
-                             dt0 + (size_t)tz * plane * ts, nullptr, nullptr, nullptr, nullptr, OF3D_DEVICE);
-            if (rc) break;
-            tz = b2;
+    // (a lambda so that every early error return still restores the context and drains the streams below)
+    auto run = [&]() -> int {
+        int64_t tz = 0;                                         // planes whose temporal stage has been enqueued
+        int ns = 0;
+        for (int64_t a = 0; a < nz; a += slab, ++ns) {
+            const int64_t b = std::min(nz, a + slab), a2 = std::max<int64_t>(0, a - H), b2 = std::min(nz, b + H);
+            if (tz < b2) {
+                // wait (on the device) for every uploaded piece that holds planes below b2
+                const size_t limit = (size_t)b2 * plane * ib;
+                cudaEvent_t ev = nullptr;
+                for (const auto& pt : c->parts) if (pt.off < limit) ev = pt.ev;
+                if (ev) OF3D_CUDA_TRY(cudaStreamWaitEvent(c->stream, ev, 0));
+                const void* frames[kMaxFrames];
+                for (int k = 0; k < t->nT; ++k) frames[k] = c->win + (size_t)k * slot + (size_t)tz * plane * ib;
+                if (int rc = flow_staged(c, 1, 3, frames, in_dtype, OF3D_DEVICE, b2 - tz, ny, nx, t, precision, flags,
+                                         ic + (size_t)tz * plane * ts, dt0 + (size_t)tz * plane * ts, nullptr, nullptr, nullptr, nullptr,
+                                         OF3D_DEVICE)) return rc;
+                tz = b2;
+            }
+            const int q = ns & 1;
+            if (ns >= 2) OF3D_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_dn[q], 0));   // the copy-back of slab ns - 2 has left the buffers
+            if (int rc = flow_staged(c, 2, 3, nullptr, in_dtype, OF3D_DEVICE, b2 - a2, ny, nx, t, precision, flags,
+                                     ic + (size_t)a2 * plane * ts, dt0 + (size_t)a2 * plane * ts, ext[q][0], ext[q][1], ext[q][2], ext[q][3],
+                                     OF3D_DEVICE)) return rc;
+            OF3D_CUDA_TRY(cudaEventRecord(c->ev_c, c->stream));
+            OF3D_CUDA_TRY(cudaStreamWaitEvent(c->s_dn, c->ev_c, 0));
+            for (int i = 0; i < 4; ++i)
+                OF3D_CUDA_TRY(cudaMemcpyAsync((char*)hout[i] + (size_t)a * plane * osz[i], ext[q][i] + (size_t)(a - a2) * plane * osz[i],
+                                              (size_t)(b - a) * plane * osz[i], cudaMemcpyDeviceToHost, c->s_dn));
+            OF3D_CUDA_TRY(cudaEventRecord(c->ev_dn[q], c->s_dn));
         }
-        const int q = ns & 1;
-        if (ns >= 2) OF3D_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_dn[q], 0));   // the copy-back of slab ns - 2 has left the buffers
-        rc = flow_staged(c, 2, 3, nullptr, in_dtype, OF3D_DEVICE, b2 - a2, ny, nx, t, precision, flags, ic + (size_t)a2 * plane * ts,
-                         dt0 + (size_t)a2 * plane * ts, ext[q][0], ext[q][1], ext[q][2], ext[q][3], OF3D_DEVICE);
-        if (rc) break;
-        OF3D_CUDA_TRY(cudaEventRecord(c->ev_c, c->stream));
-        OF3D_CUDA_TRY(cudaStreamWaitEvent(c->s_dn, c->ev_c, 0));
-        for (int i = 0; i < 4; ++i)
-            OF3D_CUDA_TRY(cudaMemcpyAsync((char*)hout[i] + (size_t)a * plane * osz[i], ext[q][i] + (size_t)(a - a2) * plane * osz[i],
-                                          (size_t)(b - a) * plane * osz[i], cudaMemcpyDeviceToHost, c->s_dn));
-        OF3D_CUDA_TRY(cudaEventRecord(c->ev_dn[q], c->s_dn));
-    }
+        return OF3D_OK;
+    };
+    const int rc = run();
     c->async = saved_async;
     cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->s_dn);
     if (rc) return rc;
