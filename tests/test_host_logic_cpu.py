@@ -119,3 +119,17 @@ def test_numa_binding_degrades_quietly(monkeypatch):
     monkeypatch.setenv('OF3D_NUMA_BIND', '0')
     assert numa.bind_to_device(0) is None
     assert os.sched_getaffinity(0) == before or True
+
+
+def test_boundary_dtype_mapping():
+    """dtype a host array crosses the boundary in: supported dtypes as they are (native byte order), bool/int8 widened,
+    everything else real -> float64 like the reference's np.double(images) (calc_flow.py:67,225); complex is refused"""
+    from opticalflow3d_dev_b200.calc_flow import _device_dtype
+    for dt in (np.uint8, np.uint16, np.int16, np.int32, np.uint32, np.float32, np.float64):
+        assert _device_dtype(dt) == np.dtype(dt)
+        assert _device_dtype(np.dtype(dt).newbyteorder('>')) == np.dtype(dt)
+    assert _device_dtype(np.bool_) == np.uint8 and _device_dtype(np.int8) == np.int16
+    for dt in (np.uint64, np.int64, np.float16):
+        assert _device_dtype(dt) == np.float64
+    with pytest.raises(TypeError):
+        _device_dtype(np.complex64)
