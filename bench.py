@@ -8,9 +8,13 @@ bench.py -- output voxels/s of the dense Lucas-Kanade hot path (calc_flow3D / ca
 A "step" is one pass of the hot path over the workload's whole synthetic time-lapse: every output
 timepoint (Nt - 2*ceil(3 tSig) of them) is computed once, sharded by output timepoint across the N
 ranks (strong scaling; no data-path collective).  `value` = output voxels of all ranks / max-over-ranks
-device time, inputs resident in HBM.  `e2e` = the same metric through the drop-in Python call
-calc_flow3D(host window) -> host arrays, host<->device copies inside the timed region, on a bounded
-number of timepoints of the same volume shape.  `cpu_baseline` / `--impl reference` = the reference's
+device time, inputs resident in HBM.  `e2e` = the same metric through the streaming engine under
+process_flow (timelapse.FlowStream: host frames in, host results out, host<->device copies inside the
+timed region, a bounded number of timepoints of the same volume shape); beside it
+`e2e.calc_flow_call_value` / `calc_flow_call_plain_numpy_value`: the synchronous drop-in call
+calc_flow3D(host window) -> host arrays with pinned / ordinary NumPy buffers.  `roofline` = the dominant
+kernel, timed live by the library's per-stage event brackets (of3d_set_profile), with every stage in
+`roofline.stages` and the whole pipeline in `roofline.pipeline`.  `cpu_baseline` / `--impl reference` = the reference's
 NumPy/SciPy algorithm (oracle port using the reference's own scipy.ndimage.correlate1d and
 numpy.linalg.eigvals calls) on the box's host cores, on a z/y/x-cropped sample of the same workload.
 Prints ONE JSON line on rank 0.
