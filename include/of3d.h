@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OF3D_VERSION 100 /* 0.1.0 */
+#define OF3D_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define OF3D_API __attribute__((visibility("default")))
@@ -168,9 +168,44 @@ OF3D_API int of3d_flow_from_dt(of3d_ctx* ctx, int ndim, const void* ic_dev, cons
                                int64_t nz, int64_t ny, int64_t nx, const of3d_taps* taps, int precision, unsigned flags,
                                void* vx, void* vy, void* vz, void* rel, int out_mem);
 
-/* Stream control: the context's stream as a cudaStream_t (for CUDA-event timing by the caller),
+/*
+ * z-slab sharding across GPUs, one process per GPU (the z-coupled stages are calc_flow.py:279-313).
+ * A rank owns the planes [z0, z1) of the volume and keeps every frame of the window in an EXTENDED buffer: `lo` halo
+ * planes below, its `own` planes, `hi` halo planes above, where lo, hi <= H = R + Rw (gradient + window radius) and 0 at
+ * the ends of the volume (clamp-to-edge applies there, calc_flow.py:279-313 mode='nearest').
+ *
+ *   of3d_comm_unique_id / of3d_comm_init / of3d_comm_destroy
+ *       the NCCL communicator of the exchange.  Rank 0 obtains a 128-byte id and distributes it by any means (the
+ *       Python host broadcasts it with torch.distributed); every rank then calls of3d_comm_init.  NCCL is loaded at
+ *       run time (libnccl.so.2), so single-GPU users need none.
+ *   of3d_halo_exchange
+ *       for each of the n_frames extended frames: sends the `send_dn` lowest owned planes to rank - 1 and the `send_up`
+ *       highest to rank + 1, receives `lo` planes from rank - 1 into [0, lo) and `hi` planes from rank + 1 into
+ *       [lo + own, lo + own + hi) -- raw planes of the input dtype, straight into place, one grouped ncclSend/ncclRecv on
+ *       a dedicated stream.  Returns at once; the next of3d_flow3d_slab waits for it on the device, and only before the
+ *       first chunk that touches a halo plane.
+ *   of3d_flow3d_slab
+ *       calc_flow3D of the planes [own_lo, own_lo + own_n) of the extended window (frames_ext[k]: DEVICE pointers,
+ *       nz_ext planes each); vx, vy, vz, rel are DEVICE buffers of own_n planes.  Every stage runs only on the planes the
+ *       owned range needs (gradients on own +- Rw, window sums and solve on own).  chunk_planes > 0 works through the
+ *       owned range in chunks of that many planes (interior chunks first, overlapping the exchange), which bounds the
+ *       workspace by the chunk instead of the slab; 0 = one chunk.  Results are bit-identical to the unsharded call.
+ */
+OF3D_API int of3d_comm_unique_id(void* id128);
+OF3D_API int of3d_comm_init(of3d_ctx* ctx, const void* id128, int nranks, int rank);
+OF3D_API int of3d_comm_destroy(of3d_ctx* ctx);
+OF3D_API int of3d_halo_exchange(of3d_ctx* ctx, void* const* frames_ext, int n_frames, size_t plane_bytes, int64_t lo, int64_t own,
+                                int64_t hi, int64_t send_dn, int64_t send_up);
+OF3D_API int of3d_flow3d_slab(of3d_ctx* ctx, const void* const* frames_ext, int in_dtype, int64_t nz_ext, int64_t ny, int64_t nx,
+                              int64_t own_lo, int64_t own_n, int64_t chunk_planes, const of3d_taps* taps, int precision,
+                              unsigned flags, void* vx, void* vy, void* vz, void* rel);
+
+/* Stream control: the context's stream as a cudaStream_t (for CUDA-event timing by the caller), a caller-supplied
+ * stream (of3d_set_stream: every later kernel and copy of the context runs on `cuda_stream`, a cudaStream_t of the
+ * context's device; NULL restores the context's own stream; the SURVEY 8(b) sketch's `void* cuda_stream` argument),
  * asynchronous mode (device in/out only: calls return after enqueueing), and a sync. */
 OF3D_API void* of3d_stream(of3d_ctx* ctx);
+OF3D_API int of3d_set_stream(of3d_ctx* ctx, void* cuda_stream);
 OF3D_API int of3d_set_async(of3d_ctx* ctx, int enable);
 OF3D_API int of3d_sync(of3d_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
@@ -184,7 +219,7 @@ OF3D_API int64_t of3d_launch_count(of3d_ctx* ctx);
  */
 #define OF3D_STAGE_TEMPORAL 0         /* calc_flow.py:276-278  temporal derivative of the centre frame          */
 #define OF3D_STAGE_GRAD_XY 1          /* calc_flow.py:279-312  in-plane passes of dx, dy, dz, dt                */
-#define OF3D_STAGE_GRAD_Z 2           /* calc_flow.py:279-312  z passes of dx, dy, dz, dt                       */
+#define OF3D_STAGE_GRAD_Z 2           /* calc_flow.py:276-312  z passes of dx, dy, dz, dt (+ fused temporal derivative) */
 #define OF3D_STAGE_WINDOW_Z 3         /* calc_flow.py:315-331  nine products and the z pass of the window       */
 #define OF3D_STAGE_WINDOW_XY_SOLVE 4  /* calc_flow.py:315-357  in-plane window passes, solve, reliability       */
 #define OF3D_STAGE_GENERIC 5          /* the same lines on the generic (any tap count / bit-exact) kernels      */
@@ -212,6 +247,13 @@ OF3D_API int of3d_order_stats(of3d_ctx* ctx, const void* data_dev, int is_f64, i
 OF3D_API int of3d_mask_derive(of3d_ctx* ctx, const void* vx, const void* vy, const void* vz, const void* rel, int v_f64, int rel_f64,
                               int64_t n, double thresh, double xyscale, double zscale, double tscale,
                               void* ox, void* oy, void* oz, void* mag, void* theta, void* phi);
+
+/*
+ * TIFF strip / tile decoders for the time-lapse driver's reader (host code, no GPU; the reference reads through tifffile,
+ * calc_flow.py:445-465,509,571, and its MATLAB twin writes LZW, src/MATLAB/TIFFwrite.m:27).  kind 0 = TIFF 6.0 LZW,
+ * 1 = PackBits.  Decodes at most `cap` bytes into dst; returns the number of bytes produced, or -1 for a corrupt stream.
+ */
+OF3D_API int64_t of3d_tiff_decode(int kind, const void* src, size_t n, void* dst, size_t cap);
 
 /*
  * Benchmark utility: fill a device buffer (nt, nz, ny, nx) of uint16 with the synthetic

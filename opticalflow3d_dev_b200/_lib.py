@@ -42,7 +42,14 @@ SIGNATURES = {
                               _vp, _vp, _vp, _vp, _i]),
     'of3d_temporal': (_i, [_vp, _i, C.POINTER(_vp), _i, _i, _i64, _i64, _i64, C.POINTER(Taps), _i, _u, _vp, _vp]),
     'of3d_flow_from_dt': (_i, [_vp, _i, _vp, _vp, _i64, _i64, _i64, C.POINTER(Taps), _i, _u, _vp, _vp, _vp, _vp, _i]),
+    'of3d_comm_unique_id': (_i, [_vp]),
+    'of3d_comm_init': (_i, [_vp, _vp, _i, _i]),
+    'of3d_comm_destroy': (_i, [_vp]),
+    'of3d_halo_exchange': (_i, [_vp, C.POINTER(_vp), _i, _sz, _i64, _i64, _i64, _i64, _i64]),
+    'of3d_flow3d_slab': (_i, [_vp, C.POINTER(_vp), _i, _i64, _i64, _i64, _i64, _i64, _i64, C.POINTER(Taps), _i, _u,
+                              _vp, _vp, _vp, _vp]),
     'of3d_stream': (_vp, [_vp]),
+    'of3d_set_stream': (_i, [_vp, _vp]),
     'of3d_set_async': (_i, [_vp, _i]),
     'of3d_sync': (_i, [_vp]),
     'of3d_launch_count': (_i64, [_vp]),
@@ -57,6 +64,7 @@ SIGNATURES = {
     'of3d_order_stats': (_i, [_vp, _vp, _i, _i64, _i64, _i64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
     'of3d_mask_derive': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
                               _vp, _vp, _vp, _vp, _vp, _vp]),
+    'of3d_tiff_decode': (_i64, [_i, _vp, _sz, _vp, _sz]),
     'of3d_synth_blobs': (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, C.c_uint64]),
 }
 

@@ -53,7 +53,7 @@ def build_library(force=False, verbose=False):
         text += ' '.join(cmd) + '\n' + out
         failed |= p.returncode != 0
     if not failed:
-        cmd = [nvcc, '-shared', '-o', LIB + '.tmp'] + [obj for _, obj, _ in procs]
+        cmd = [nvcc, '-shared', '-o', LIB + '.tmp'] + [obj for _, obj, _ in procs] + ['-ldl']
         res = subprocess.run(cmd, capture_output=True, text=True)
         text += ' '.join(cmd) + '\n' + res.stdout + res.stderr
         failed = res.returncode != 0

@@ -53,7 +53,8 @@ struct Shape {
 // The opaque context of the C ABI.
 struct of3d_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // the stream every kernel of the context runs on
+    cudaStream_t own_stream = nullptr;   // created with the context; `stream` is this one unless the caller lent its own
     char* ws = nullptr;   // device workspace
     size_t ws_cap = 0;
     size_t ws_off = 0;    // bump pointer (reset every call)
@@ -72,6 +73,12 @@ struct of3d_ctx {
     char* pipe = nullptr;                               // ic, dt0 and two sets of slab outputs of the pipelined host call
     size_t pipe_cap = 0;
     cudaEvent_t ev_c = nullptr, ev_dn[2] = {nullptr, nullptr};
+    // z-slab sharding: NCCL communicator (loaded at run time) and the halo-exchange stream
+    void* comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    cudaStream_t s_comm = nullptr;
+    cudaEvent_t ev_halo = nullptr, ev_ready = nullptr;
+    bool halo_pending = false;                          // an exchange is in flight: slab calls wait for it where they need the halo
     // optional per-stage device timing (of3d_set_profile): every launch is bracketed by events on `stream`
     int profile = 0;
     std::vector<cudaEvent_t> ev_pool;                 // recycled events
@@ -112,8 +119,11 @@ static inline P* ws_take(of3d_ctx* c, size_t count) {
 // Marching-kernel pipeline (pipeline_fast.cuh): returns OF3D_OK, an error, or kNotSupported when the
 // tap counts have no specialised instantiation (the caller then runs the generic pipeline).
 constexpr int kNotSupported = 1;
+// Flow of the planes [own_lo, own_lo + own_n) of the volume s (3D; own_lo = 0, own_n = 1 in 2D); the outputs hold own_n
+// planes.  Temporal stage: raw frames `fp` of `in_dtype` (3D only, when fused_temporal_ok) or (ic, dt0) volumes.
 template <typename T>
-int run_fast(of3d_ctx* c, const Shape& s, const T* ic, const T* dt0, const of3d_taps* t, T* vx, T* vy, T* vz, T* rel);
+int run_fast(of3d_ctx* c, const Shape& s, const FramePtrs* fp, int in_dtype, const T* ic, const T* dt0, const of3d_taps* t,
+             int64_t own_lo, int64_t own_n, T* vx, T* vy, T* vz, T* rel, int rel_f32);
 
 // Tap-count classes with a specialised marching instantiation (shorter filters are zero-padded to the class)
 static inline int spatial_class(const of3d_taps* t) {
@@ -141,9 +151,17 @@ static inline bool fast_supported(const of3d_taps* t) {
     return spatial_class(t) >= 0 && window_class(t) >= 0 && taps_symmetric(t->S, t->nS, 1.0) && taps_symmetric(t->G, t->nG, 1.0) &&
            taps_symmetric(t->W, t->nW, 1.0) && taps_symmetric(t->D, t->nD, -1.0);
 }
-// workspace volumes of compute type used by run_fast (excluding ic and dt0)
+// workspace volumes of compute type used by run_fast on a whole volume (excluding ic and dt0)
 static inline int fast_volumes(int ndim) { return ndim == 3 ? 9 + 4 : 3; }
-// the gradient volumes carry up to kMaxZPad replicated planes beyond each z face for the TMA-fed window march
-constexpr int kMaxZPad = 12;
+// The z march can read the raw frames itself (kernels_tz.cuh) when they are 8/16-bit integers, every frame and row is
+// 16-byte aligned, the window has at most kFusedMaxFrames frames and T is antisymmetric bit for bit with a zero centre
+constexpr int kFusedMaxFrames = 24;
+static inline bool fused_temporal_ok(const of3d_taps* t, const FramePtrs& fp, int in_dtype, int64_t nx) {
+    const int sz = in_dtype == OF3D_U8 ? 1 : ((in_dtype == OF3D_U16 || in_dtype == OF3D_I16) ? 2 : 0);
+    if (!sz || t->nT > kFusedMaxFrames || (nx * sz) % 16 != 0 || !taps_symmetric(t->T, t->nT, -1.0) || t->T[t->nT / 2] != 0.0) return false;
+    for (int k = 0; k < t->nT; ++k)
+        if (reinterpret_cast<uintptr_t>(fp.p[k]) % 16) return false;
+    return true;
+}
 
 }  // namespace of3d

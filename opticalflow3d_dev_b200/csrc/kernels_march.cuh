@@ -34,6 +34,7 @@ struct MarchGeom {
     int64_t stride_march;  // element stride of the filtered axis (input and plain output)
     int64_t stride_other;  // element stride of the remaining axis (same for the transposed output)
     int64_t vol;           // elements per volume (channel stride)
+    int m_begin, m_end;    // outputs [m_begin, m_end) of the filtered axis are produced (inputs clamp to [0, n_march))
     int chunk;             // outputs per task along the filtered axis (multiple of 32)
     int n_chunks;
     int lane_groups;       // ceil(n_lane / 32)
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(WPB * 32) march_window(const WindowArgs<T, K> 
     const int64_t lane0 = (int64_t)lg * 32;
     const bool lane_ok = lane0 + lane < g.n_lane;
     const int64_t lpos = lane_ok ? lane0 + lane : g.n_lane - 1;   // out-of-range lanes read a valid address
-    const int c0 = chunk * g.chunk;
-    const int c1 = min(c0 + g.chunk, (int)g.n_march);
+    const int c0 = g.m_begin + chunk * g.chunk;
+    const int c1 = min(c0 + g.chunk, g.m_end);
     const int64_t base = other * g.stride_other + lpos;
 
     Pre pre;
@@ -182,8 +183,8 @@ __global__ void __launch_bounds__(WPB * 32) march_window(const WindowArgs<T, K> 
     T acc[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) acc[i] = T(0);
-    // store position of the output completed at step s: c0 + s - 2R
-    char* optr = reinterpret_cast<char*>(outc + base) + ((int64_t)c0 - 2 * R) * pre.stride_bytes;
+    // store position of the output completed at step s: c0 + s - 2R (plane 0 of the output is m_begin)
+    char* optr = reinterpret_cast<char*>(outc + base) + ((int64_t)(c0 - g.m_begin) - 2 * R) * pre.stride_bytes;
 
     // The value of step s+1 is read from the ring while step s is being accumulated (software pipelining:
     // the LDS latency hides under the K FMAs of the current step).
@@ -204,104 +205,6 @@ __global__ void __launch_bounds__(WPB * 32) march_window(const WindowArgs<T, K> 
         }
     }
     cp_async_wait<0>();
-}
-
-// ------------------------------------------------------------------------------------------------
-// Gradient z pass (calc_flow.py:279-288, z passes): {B0, B1, B2, B3} -> {G B0, S B1, S B2, D B3} = {dt, dy, dx, dz}.
-// Run as two launches of a two-stream march -- (G on B0, D on B3) with KR taps and (S on B1, S on B2) with KS
-// taps: two streams keep the accumulators at 2K registers, four would need 250 and halve the occupancy.
-template <typename T, int K>
-struct PairArgs {
-    MarchGeom g;
-    Taps<T, K> f0, f1;
-    const T* in[2];
-    T* out[2];
-    int pad;          // > 0: also write `pad` copies of the first / last output plane beyond the z faces (the outputs
-                      // are then volumes with pad extra planes on either side; see kernels_tma.cuh)
-};
-
-template <typename T, int DEPTH, int WPB>
-constexpr size_t pair_smem() { return (size_t)WPB * Prefetcher<T, 2, DEPTH>::elems_per_warp * sizeof(T); }
-
-// SYM0 / SYM1: symmetry of f0 / f1 (+1 symmetric, -1 antisymmetric)
-template <typename T, int K, int P, int DEPTH, int WPB, int SYM0, int SYM1>
-__global__ void __launch_bounds__(WPB * 32) march_pair(const PairArgs<T, K> a) {
-    static_assert(P >= K && P % DEPTH == 0, "bad unroll period");
-    constexpr int R = K / 2;
-    using Pre = Prefetcher<T, 2, DEPTH>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const MarchGeom& g = a.g;
-    int64_t task = (int64_t)blockIdx.x * WPB + warp;
-    const int64_t ntasks = (int64_t)g.n_other * g.lane_groups * g.n_chunks;
-    if (task >= ntasks) return;
-    const int chunk = (int)(task % g.n_chunks); task /= g.n_chunks;
-    const int lg = (int)(task % g.lane_groups);
-    const int64_t other = task / g.lane_groups;
-    const int64_t lane0 = (int64_t)lg * 32;
-    const bool lane_ok = lane0 + lane < g.n_lane;
-    const int64_t lpos = lane_ok ? lane0 + lane : g.n_lane - 1;
-    const int c0 = chunk * g.chunk;
-    const int c1 = min(c0 + g.chunk, (int)g.n_march);
-    const int64_t base = other * g.stride_other + lpos;
-
-    Pre pre;
-    pre.lbase = reinterpret_cast<T*>(smem_raw) + warp * Pre::elems_per_warp + lane;
-    pre.sbase = (uint32_t)__cvta_generic_to_shared(pre.lbase);
-    pre.qpos = c0 - R;
-    pre.n_march_m1 = (int)g.n_march - 1;
-    pre.stride_bytes = g.stride_march * (int64_t)sizeof(T);
-    const int64_t off0 = base + clampi(c0 - R, g.n_march) * g.stride_march;
-    pre.gp[0] = reinterpret_cast<const char*>(a.in[0] + off0);
-    pre.gp[1] = reinterpret_cast<const char*>(a.in[1] + off0);
-
-    const int nout = c1 - c0;
-    const unsigned nvalid = lane_ok ? (unsigned)nout : 0u;
-    const int nsteps = (nout + 2 * R + P - 1) / P * P;     // padded to whole periods: no branch in the unrolled body
-#pragma unroll
-    for (int d = 0; d < DEPTH - 1; ++d) pre.issue(d);
-
-    T acc0[P], acc1[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) { acc0[i] = T(0); acc1[i] = T(0); }
-    // byte offset of the output completed at step s: c0 + s - 2R
-    int64_t ooff = base * (int64_t)sizeof(T) + ((int64_t)c0 - 2 * R) * pre.stride_bytes;
-
-    cp_async_wait<DEPTH - 2>();
-    T vn0 = pre.read(0, 0), vn1 = pre.read(0, 1);
-#pragma unroll 1
-    for (int s0 = 0; s0 < nsteps; s0 += P) {
-#pragma unroll
-        for (int ph = 0; ph < P; ++ph) {
-            const T v0 = vn0, v1 = vn1;
-            pre.issue((ph + DEPTH - 1) % DEPTH);
-            cp_async_wait<DEPTH - 2>();            // step s+1 has landed: read it while step s is accumulated
-            vn0 = pre.read((ph + 1) % DEPTH, 0);
-            vn1 = pre.read((ph + 1) % DEPTH, 1);
-            const T r0 = ring_push<T, K, P, SYM0>(acc0, a.f0, v0, ph);
-            const T r1 = ring_push<T, K, P, SYM1>(acc1, a.f1, v1, ph);
-            if ((unsigned)(s0 + ph - 2 * R) < nvalid) {
-                *reinterpret_cast<T*>(reinterpret_cast<char*>(a.out[0]) + ooff) = r0;
-                *reinterpret_cast<T*>(reinterpret_cast<char*>(a.out[1]) + ooff) = r1;
-            }
-            ooff += pre.stride_bytes;
-        }
-    }
-    cp_async_wait<0>();
-    // replicated planes beyond the z faces (each lane copies the values it stored itself)
-    if (a.pad > 0 && lane_ok) {
-#pragma unroll 1
-        for (int face = 0; face < 2; ++face) {
-            if (face == 0 ? c0 != 0 : c1 != (int)g.n_march) continue;
-            const int64_t z = face == 0 ? 0 : g.n_march - 1, dir = face == 0 ? -1 : 1;
-#pragma unroll 1
-            for (int q = 0; q < 2; ++q) {
-                T* o = a.out[q] + base + z * g.stride_march;
-                const T v = *o;
-                for (int j = 1; j <= a.pad; ++j) o[dir * j * g.stride_march] = v;
-            }
-        }
-    }
 }
 
 }  // namespace of3d

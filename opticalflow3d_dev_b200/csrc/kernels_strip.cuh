@@ -10,8 +10,7 @@
 //   march   filter along y: lane = column; the gathered value of each of the RB rows is scattered into K register
 //           accumulators (the statically rotated ring of kernels_march.cuh).
 //
-// strip_grad          gradient stage: (dt0, ic) -> the four pre-z gradient volumes (calc_flow.py:279-288 x and y
-//                     passes) or, in 2D, dt, dy, dx (calc_flow.py:116-122).  Three independent warp roles.
+// strip_conv2         gradient stage, in-plane passes of one gradient volume (calc_flow.py:279-288 / 116-122).
 // strip_window_solve  window x pass + y pass + per-voxel solve (calc_flow.py:300-357 / 133-168): the NCH window
 //                     sums of a voxel only ever exist in registers and shared memory.
 #pragma once
@@ -218,56 +217,55 @@ struct StripStage16 {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Gradient stage.  Roles (one warp each, independent):
-//   0  in dt0: gather G_x, march G_y                      -> out0            (dt before the z pass / dt in 2D)
-//   1  in ic : gather S_x, march D_y -> out1 (dy path) and, in 3D, march S_y -> out3 (dz path)
-//   2  in ic : gather D_x, march S_y                      -> out2            (dx path)
-template <typename T, int KR, int KS>
-struct GradStripArgs {
+// In-plane passes of one gradient volume: gather with the x filter fg (KG taps), march with the y filter fa (KA taps).
+// The gradient stage is four instantiations (calc_flow.py:279-288 x and y passes; z ran first, kernels_tz.cuh):
+//     dt = G_y G_x C      dy = D_y S_x A      dx = S_y D_x A      dz = S_y S_x Bz
+// and in 2D (calc_flow.py:116-122)  dt = G_y G_x dt0, dy = D_y S_x Ic, dx = S_y D_x Ic.  Every instantiation stages
+// only the halo its own x filter needs and unrolls only the period its own y filter needs.
+template <typename T, int KG, int KA>
+struct Conv2Args {
     StripGeom g;
-    Taps<T, KR> fG, fD;
-    Taps<T, KS> fS;
-    const T* dt0; const T* ic;
-    T* out[4];              // out[3] == nullptr in 2D
+    Taps<T, KG> fg;
+    Taps<T, KA> fa;
+    const T* in;
+    T* out;
 };
 
-template <typename T, int KR, bool V16 = false>
-constexpr size_t grad_strip_smem(int wpb) {
-    if constexpr (V16) return (size_t)wpb * StripStage16<T, KR>::elems * sizeof(T);
-    else return (size_t)wpb * StripStage<T, KR, 1, 2>::elems * sizeof(T);
+template <typename T, int KG, bool V16 = false>
+constexpr size_t conv2_smem(int wpb) {
+    if constexpr (V16) return (size_t)wpb * StripStage16<T, KG>::elems * sizeof(T);
+    else return (size_t)wpb * StripStage<T, KG, 1, 2>::elems * sizeof(T);
 }
 
-// One role.  Each role is its own kernel instantiation: dispatched inside one kernel the three bodies get a merged
-// register allocation of 228 registers (8 warps per SM); separately they need 56-95.
-template <typename T, int KR, int KS, int P, int ROLE, bool V16>
-__device__ __forceinline__ void strip_grad_body(const GradStripArgs<T, KR, KS>& a, T* smem_warp, int strip, int chunk, int o) {
-    constexpr int RB = kStripRB, R = KR / 2, RS = KS / 2;
-    constexpr int KGATHER = ROLE == 1 ? KS : KR;            // taps of the x filter
-    constexpr int KA = ROLE == 2 ? KS : KR;                 // taps of the (first) y filter
-    constexpr int lagA = R + KA / 2;                        // the stream with radius rf completes row m0 + s - R - rf
-    using Stage = typename std::conditional<V16, StripStage16<T, KR>, StripStage<T, KR, 1, 2>>::type;
+// SYMG / SYMA: +1 symmetric, -1 antisymmetric taps (only half of them are read)
+template <typename T, int KG, int SYMG, int KA, int SYMA, int WPB, bool V16 = false>
+__global__ void __launch_bounds__(WPB * 32) strip_conv2(const Conv2Args<T, KG, KA> a) {
+    constexpr int RB = kStripRB, RA = KA / 2, P = (KA + RB - 1) / RB * RB;
+    using Stage = typename std::conditional<V16, StripStage16<typename std::conditional<V16, T, double>::type, KG>, StripStage<T, KG, 1, 2>>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const StripGeom& g = a.g;
-    const int lane = threadIdx.x & 31;
+    int64_t task = (int64_t)blockIdx.x * WPB + warp;
+    const int nstrips = (g.n_c + 31) / 32;
+    if (task >= (int64_t)nstrips * g.n_chunks * g.n_o) return;
+    const int strip = (int)(task % nstrips); task /= nstrips;
+    const int chunk = (int)(task % g.n_chunks);
+    const int o = (int)(task / g.n_chunks);
     const int cw0 = strip * 32;
     const int m0 = chunk * g.chunk;
     const int nout = min(m0 + g.chunk, g.n_m) - m0;
-    const int nsteps = (nout + 2 * R + P - 1) / P * P;
+    const int nsteps = (nout + 2 * RA + P - 1) / P * P;
     const unsigned nvalid = (cw0 + lane < g.n_c) ? (unsigned)nout : 0u;
 
     Stage st;
-    st.init(smem_warp, cw0, m0 - R, g);
-    if constexpr (V16) st.src = (ROLE == 0 ? a.dt0 : a.ic) + (int64_t)o * g.stride_o;
-    else st.src[0] = (ROLE == 0 ? a.dt0 : a.ic) + (int64_t)o * g.stride_o;
-    const int64_t obase = (int64_t)o * g.stride_o + cw0 + lane;
-    T* const oA = a.out[ROLE == 0 ? 0 : (ROLE == 1 ? 1 : 2)] + obase;
-    T* const oB = (ROLE == 1 && a.out[3]) ? a.out[3] + obase : nullptr;   // second stream of role 1: S_y (3D only)
-    const Taps<T, KR>& fyA = ROLE == 0 ? a.fG : a.fD;                      // y filter of roles 0 and 1
+    st.init(reinterpret_cast<T*>(smem_raw) + warp * Stage::elems, cw0, m0 - RA, g);
+    if constexpr (V16) st.src = a.in + (int64_t)o * g.stride_o;
+    else st.src[0] = a.in + (int64_t)o * g.stride_o;
+    T* const op = a.out + (int64_t)o * g.stride_o + cw0 + lane;
 
-    T accA[P], accB[ROLE == 1 ? P : 1];
+    T acc[P];
 #pragma unroll
-    for (int i = 0; i < P; ++i) accA[i] = T(0);
-#pragma unroll
-    for (int i = 0; i < (ROLE == 1 ? P : 1); ++i) accB[i] = T(0);
+    for (int i = 0; i < P; ++i) acc[i] = T(0);
 
     st.issue(0);
     st.issue(1);
@@ -280,13 +278,9 @@ __device__ __forceinline__ void strip_grad_body(const GradStripArgs<T, KR, KS>& 
             __syncwarp();
             if constexpr (V16) {
                 st.fix_edges(b);
-                if (ROLE == 0) st.template gather<KR, 1>(a.fG, b);
-                else if (ROLE == 1) st.template gather<KS, 1>(a.fS, b);
-                else st.template gather<KR, -1>(a.fD, b);
+                st.template gather<KG, SYMG>(a.fg, b);
             } else {
-                if (ROLE == 0) st.template gather<KR, false>(a.fG, 0, b);
-                else if (ROLE == 1) st.template gather<KS, false>(a.fS, 0, b);
-                else st.template gather<KR, false>(a.fD, 0, b);
+                st.template gather<KG, false>(a.fg, 0, b);
             }
             __syncwarp();
             st.issue(b + 2);                                                  // into the buffer just consumed
@@ -294,37 +288,13 @@ __device__ __forceinline__ void strip_grad_body(const GradStripArgs<T, KR, KS>& 
             for (int r = 0; r < RB; ++r) {
                 const int ph = bi * RB + r;
                 const int s = s0 + ph;
-                const T v = st.gathered(r);
-                T resA;
-                if (ROLE == 2) resA = ring_push<T, KS, P, 1>(accA, a.fS, v, ph);
-                else resA = ring_push<T, KR, P, (ROLE == 0 ? 1 : -1)>(accA, fyA, v, ph);
-                if ((unsigned)(s - lagA) < nvalid) oA[(int64_t)(m0 + s - lagA) * g.stride_m] = resA;
-                if (ROLE == 1) {
-                    const T resB = ring_push<T, KS, P, 1>(*reinterpret_cast<T(*)[P]>(accB), a.fS, v, ph);
-                    if (oB && (unsigned)(s - R - RS) < nvalid) oB[(int64_t)(m0 + s - R - RS) * g.stride_m] = resB;
-                }
+                const T res = ring_push<T, KA, P, SYMA>(acc, a.fa, st.gathered(r), ph);
+                if ((unsigned)(s - 2 * RA) < nvalid) op[(int64_t)(m0 + s - 2 * RA) * g.stride_m] = res;
             }
             __syncwarp();                                                     // gathered rows consumed before the next gather
         }
     }
-    (void)KGATHER;
     cp_async_wait<0>();
-}
-
-template <typename T, int KR, int KS, int P, int ROLE, int WPB, bool V16 = false>
-__global__ void __launch_bounds__(WPB * 32) strip_grad(const GradStripArgs<T, KR, KS> a) {
-    static_assert(P >= KR && KR >= KS && P % kStripRB == 0, "bad unroll period");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5;
-    const StripGeom& g = a.g;
-    int64_t task = (int64_t)blockIdx.x * WPB + warp;
-    const int nstrips = (g.n_c + 31) / 32;
-    if (task >= (int64_t)nstrips * g.n_chunks * g.n_o) return;
-    const int strip = (int)(task % nstrips); task /= nstrips;
-    const int chunk = (int)(task % g.n_chunks);
-    const int o = (int)(task / g.n_chunks);
-    constexpr int kElems = V16 ? StripStage16<typename std::conditional<V16, T, double>::type, KR>::elems : StripStage<T, KR, 1, 2>::elems;
-    strip_grad_body<T, KR, KS, P, ROLE, V16>(a, reinterpret_cast<T*>(smem_raw) + warp * kElems, strip, chunk, o);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -340,6 +310,7 @@ struct StripArgs {
     Taps<T, K> f;
     const T* in[4];         // !PROD: in[0] = channel-major window sums of the z pass; PROD: gradients {dt, dx, dy, -}
     T* vx; T* vy; T* vz; T* rel;
+    int rel_f32;            // fp64 only: `rel` is a float buffer, the dtype the reference returns in 3D (calc_flow.py:355-357)
 };
 
 template <int NCH, int NHALF> constexpr int strip_parkrow() { return NCH * NHALF * 32 + 2; }
@@ -375,7 +346,7 @@ __device__ __forceinline__ int solve_unit(int warp, int ui) {
 // dependency chains per lane) and store the results.
 template <typename T, int NCH, int TX, int R, int NU = 1>
 __device__ __forceinline__ void solve_unit_voxels(const T* park, int parkrow, int b, int unit, int lane, int cs0, int nout, int n_c,
-                                                  int64_t plane_off, int64_t stride_m, int m0, T* vx, T* vy, T* vz, T* rel) {
+                                                  int64_t plane_off, int64_t stride_m, int m0, T* vx, T* vy, T* vz, T* rel, int rel_f32) {
     constexpr int RB = kStripRB;
     bool ok[NU];
     const T* qv[NU];
@@ -399,13 +370,19 @@ __device__ __forceinline__ void solve_unit_voxels(const T* park, int parkrow, in
                                   (double)qv[u][5 * TX], (double)qv[u][6 * TX], (double)qv[u][7 * TX], (double)qv[u][8 * TX]);
 #pragma unroll
         for (int u = 0; u < NU; ++u)
-            if (ok[u]) { vx[idx[u]] = (T)rr[u].vx; vy[idx[u]] = (T)rr[u].vy; vz[idx[u]] = (T)rr[u].vz; rel[idx[u]] = (T)rr[u].rel; }
+            if (ok[u]) {
+                vx[idx[u]] = (T)rr[u].vx; vy[idx[u]] = (T)rr[u].vy; vz[idx[u]] = (T)rr[u].vz;
+                if (sizeof(T) == 8 && rel_f32) reinterpret_cast<float*>(rel)[idx[u]] = (float)rr[u].rel;   // rounded once
+                else rel[idx[u]] = (T)rr[u].rel;
+            }
     } else {
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
             if (!ok[u]) continue;
             const Flow2 rr = solve2<false>((double)qv[u][0], (double)qv[u][TX], (double)qv[u][2 * TX], (double)qv[u][3 * TX], (double)qv[u][4 * TX]);
-            vx[idx[u]] = (T)rr.vx; vy[idx[u]] = (T)rr.vy; rel[idx[u]] = (T)rr.rel;
+            vx[idx[u]] = (T)rr.vx; vy[idx[u]] = (T)rr.vy;
+            if (sizeof(T) == 8 && rel_f32) reinterpret_cast<float*>(rel)[idx[u]] = (float)rr.rel;
+            else rel[idx[u]] = (T)rr.rel;
         }
     }
 }
@@ -478,7 +455,7 @@ __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const 
                 const int unit = solve_unit<NCH, NHALF>(warp, ui);
                 if (unit < 0) break;
                 solve_unit_voxels<T, NCH, TX, R>(park, PARKROW, b, unit, lane, cs0, nout, g.n_c, (int64_t)o * g.stride_o, g.stride_m, m0,
-                                                 a.vx, a.vy, a.vz, a.rel);
+                                                 a.vx, a.vy, a.vz, a.rel, a.rel_f32);
             }
         }
     }

@@ -7,8 +7,10 @@
 // (cp.async.bulk.tensor, the TMA engine: no LSU instruction per lane, no L1 wavefronts) into a shared-memory ring of
 // STAGES stages, completion tracked by an mbarrier transaction count; the channel warps wait on the stage's "full"
 // barrier, march ZT steps out of shared memory and release the stage on its "empty" barrier.
-// TMA fills out-of-range elements with zeros, scipy's mode='nearest' wants the edge plane: the gradient volumes
-// therefore carry R replicated planes beyond each z face (written by march_pair), so every tile is in range in z.
+// TMA fills out-of-range elements with zeros, scipy's mode='nearest' wants the edge plane: a stage that reaches beyond
+// a z face is fetched plane by plane (ZT copies of a one-plane box, z clamped) instead of as one ZT-plane box.  The
+// tensor map orders the dimensions (x, y, volume, z), so that a stage is [z][volume][x] in shared memory and a
+// one-plane box lands on one contiguous z slice of it.
 // (Row-by-row cp.async.bulk copies with clamped addresses were tried first: 64 copies of 256 B per stage ran at
 // ~80 cycles per copy, 0.9 TB/s over the chip.)
 #pragma once
@@ -43,18 +45,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Products + window z pass (calc_flow.py:300-313, z passes), all nine channels of a (y, 64 x) column per block:
-// 18 marching warps (channel ch = warp % 9 of 32-column group warp / 9) + one producer warp.  The producer loop lives in
+// Products + window z pass (calc_flow.py:300-313, z passes), all nine channels of a (y, 32 NG x) column per block:
+// 9 NG marching warps (channel ch = warp % 9 of 32-column group warp / 9) + one producer warp.  The producer loop lives in
 // a __noinline__ function: inlined anywhere in the kernel it makes ptxas move the taps from uniform registers to 50
 // vector registers (168 registers unbounded, spills at the 96 the block size allows).
+// NG = 2 (19 warps, 104 registers) up to 25 taps in fp64 and for every fp32 window; NG = 1 (10 warps) for the long fp64
+// windows whose accumulator ring alone needs 80-112 registers.
 constexpr int kTmaZT = 8;        // z steps per stage
 constexpr int kTmaStages = 4;
-constexpr int kTmaGroups = 2;    // 32-column groups per block
-constexpr int kTmaWarps = 9 * kTmaGroups + 1;
-constexpr int kTmaTX = 32 * kTmaGroups;
 
-template <typename T>
-constexpr size_t window_tma_smem() { return (size_t)kTmaStages * 4 * kTmaZT * kTmaTX * sizeof(T) + 2 * kTmaStages * 8; }
+template <typename T, int NG>
+constexpr size_t window_tma_smem() { return (size_t)kTmaStages * 4 * kTmaZT * 32 * NG * sizeof(T) + 2 * kTmaStages * 8; }
 
 // One block per (y, column group, z chunk) task.  (Persistent blocks striding over the tasks, so that the ring never
 // drains between tasks, and a 6-stage ring were measured 3 % slower: the task bookkeeping costs registers the marching
@@ -62,41 +63,49 @@ constexpr size_t window_tma_smem() { return (size_t)kTmaStages * 4 * kTmaZT * kT
 struct TmaTask {
     int x0, y, c0, nout, nstages;
 };
-template <int K>
-__device__ __forceinline__ TmaTask tma_task(int n_chunks, int lane_groups, int chunk_len, int n_march, int task) {
+template <int K, int NG>
+__device__ __forceinline__ TmaTask tma_task(int n_chunks, int lane_groups, int chunk_len, int m_begin, int m_end, int task) {
     TmaTask t;
     const int chunk = task % n_chunks; task /= n_chunks;
-    const int ngrp = (lane_groups + kTmaGroups - 1) / kTmaGroups;
-    t.x0 = (task % ngrp) * kTmaTX;
+    const int ngrp = (lane_groups + NG - 1) / NG;
+    t.x0 = (task % ngrp) * 32 * NG;
     t.y = task / ngrp;
-    t.c0 = chunk * chunk_len;
-    t.nout = min(t.c0 + chunk_len, n_march) - t.c0;
+    t.c0 = m_begin + chunk * chunk_len;
+    t.nout = min(t.c0 + chunk_len, m_end) - t.c0;
     t.nstages = (t.nout + 2 * (K / 2) + kTmaZT - 1) / kTmaZT;
     return t;
 }
 
-template <typename T, int K>
-__device__ __noinline__ void window_tma_producer(const CUtensorMap* tmap, int n_chunks, int lane_groups, int chunk_len, int n_march,
-                                                 uint32_t ring_s, uint32_t bar_s) {
-    constexpr int ZT = kTmaZT, ST = kTmaStages;
-    constexpr uint32_t kStageBytes = 4 * ZT * kTmaTX * sizeof(T);
+// tm8: box {32 NG, 1, 4, ZT}; tm1: box {32 NG, 1, 4, 1} over the same tensor
+template <typename T, int K, int NG>
+__device__ __noinline__ void window_tma_producer(const CUtensorMap* tm8, const CUtensorMap* tm1, int n_chunks, int lane_groups, int chunk_len,
+                                                 int m_begin, int m_end, int nz, uint32_t ring_s, uint32_t bar_s) {
+    constexpr int ZT = kTmaZT, ST = kTmaStages, R = K / 2;
+    constexpr uint32_t kPlaneBytes = 4 * 32 * NG * sizeof(T);
+    constexpr uint32_t kStageBytes = ZT * kPlaneBytes;
     if ((threadIdx.x & 31) != 0) return;
-    const TmaTask t = tma_task<K>(n_chunks, lane_groups, chunk_len, n_march, blockIdx.x);
+    const TmaTask t = tma_task<K, NG>(n_chunks, lane_groups, chunk_len, m_begin, m_end, blockIdx.x);
     for (int it = 0; it < t.nstages; ++it) {
         const int slot = it % ST;
         if (it >= ST) mbar_wait(bar_s + 8 * (ST + slot), ((it / ST) - 1) & 1);       // every marching warp released the slot
         mbar_arrive_expect_tx(bar_s + 8 * slot, kStageBytes);
-        // logical z of the first input is c0 - R; the padded volume starts at logical -R
-        tma_load_4d(ring_s + slot * kStageBytes, tmap, t.x0, t.y, t.c0 + it * ZT, 0, bar_s + 8 * slot);
+        const int z0 = t.c0 - R + it * ZT;                                            // first input plane of the stage
+        if (z0 >= 0 && z0 + ZT <= nz) {
+            tma_load_4d(ring_s + slot * kStageBytes, tm8, t.x0, t.y, 0, z0, bar_s + 8 * slot);
+        } else {
+            for (int r = 0; r < ZT; ++r)                                               // clamp-to-edge (scipy mode='nearest')
+                tma_load_4d(ring_s + slot * kStageBytes + r * kPlaneBytes, tm1, t.x0, t.y, 0, max(0, min(z0 + r, nz - 1)), bar_s + 8 * slot);
+        }
     }
 }
 
-// tmap: {x, y, z + 2R planes, 4 volumes} over the padded gradient volumes {dt, dx, dy, dz}, box {64, 1, ZT, 4}
-template <typename T, int K, int P>
-__global__ void __launch_bounds__(kTmaWarps * 32, 1) march_window_tma(const WindowArgs<T, K> a, const __grid_constant__ CUtensorMap tmap) {
+// tensor maps: {x, y, 4 volumes, z} over the gradient volumes {dt, dx, dy, dz}
+template <typename T, int K, int P, int NG>
+__global__ void __launch_bounds__((9 * NG + 1) * 32, 1) march_window_tma(const WindowArgs<T, K> a, const __grid_constant__ CUtensorMap tm8,
+                                                                          const __grid_constant__ CUtensorMap tm1) {
     static_assert(P >= K && P % kTmaZT == 0, "bad unroll period");
-    constexpr int R = K / 2, ZT = kTmaZT, ST = kTmaStages, NG = kTmaGroups, TX = kTmaTX;
-    constexpr int kStageElems = 4 * ZT * TX;                 // [volume][z][x]
+    constexpr int R = K / 2, ZT = kTmaZT, ST = kTmaStages, TX = 32 * NG;
+    constexpr int kStageElems = 4 * ZT * TX;                 // [z][volume][x]
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* ring = reinterpret_cast<T*>(smem_raw);
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
@@ -111,7 +120,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 1) march_window_tma(const Wind
     __syncthreads();
 
     if (warp == 9 * NG) {
-        window_tma_producer<T, K>(&tmap, g.n_chunks, g.lane_groups, g.chunk, (int)g.n_march, ring_s, bar_s);
+        window_tma_producer<T, K, NG>(&tm8, &tm1, g.n_chunks, g.lane_groups, g.chunk, g.m_begin, g.m_end, (int)g.n_march, ring_s, bar_s);
         return;
     }
 
@@ -120,20 +129,20 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 1) march_window_tma(const Wind
     // channel -> gradient pair {xx,xy,xz,yy,yz,zz,tx,ty,tz} over {dt,dx,dy,dz}
     const int ia = ch < 3 ? 1 : (ch < 5 ? 2 : (ch == 5 ? 3 : ch - 5));
     const int ib = ch < 3 ? ch + 1 : (ch < 5 ? ch - 1 : (ch == 5 ? 3 : 0));
-    const T* sa = ring + (ia * ZT) * TX + grp * 32 + lane;
-    const T* sb = ring + (ib * ZT) * TX + grp * 32 + lane;
+    const T* sa = ring + ia * TX + grp * 32 + lane;
+    const T* sb = ring + ib * TX + grp * 32 + lane;
     const int64_t stride_bytes = g.stride_march * (int64_t)sizeof(T);
 
     T acc[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) acc[i] = T(0);
 
-    const TmaTask t = tma_task<K>(g.n_chunks, g.lane_groups, g.chunk, (int)g.n_march, blockIdx.x);
+    const TmaTask t = tma_task<K, NG>(g.n_chunks, g.lane_groups, g.chunk, g.m_begin, g.m_end, blockIdx.x);
     const int64_t lane0 = (int64_t)t.x0 + grp * 32;
     const unsigned nvalid = lane0 + lane < g.n_lane ? (unsigned)t.nout : 0u;
-    // store position of the output completed at step s: c0 + s - 2R
+    // store position of the output completed at step s: c0 + s - 2R (plane 0 of the output is m_begin)
     char* optr = reinterpret_cast<char*>(a.out + (int64_t)ch * g.vol + (int64_t)t.y * g.stride_other + lane0 + lane) +
-                 ((int64_t)t.c0 - 2 * R) * stride_bytes;
+                 ((int64_t)(t.c0 - g.m_begin) - 2 * R) * stride_bytes;
     int it = 0;
 #pragma unroll 1
     for (int s0 = 0;; s0 += P) {
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 1) march_window_tma(const Wind
 #pragma unroll
             for (int r = 0; r < ZT; ++r) {
                 const int ph = sg * ZT + r;
-                const T v = pa[r * TX] * pb[r * TX];
+                const T v = pa[r * 4 * TX] * pb[r * 4 * TX];
                 const T res = ring_push<T, K, P, 1>(acc, a.f, v, ph);
                 if ((unsigned)(s0 + ph - 2 * R) < nvalid) *reinterpret_cast<T*>(optr) = res;
                 optr += stride_bytes;

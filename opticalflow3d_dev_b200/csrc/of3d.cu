@@ -8,6 +8,7 @@
 #include <string>
 #include <cstdlib>
 #include <vector>
+#include <dlfcn.h>
 
 #include "common.cuh"
 #include "kernels_analysis.cuh"
@@ -79,18 +80,27 @@ static int ws_ensure(of3d_ctx* c, size_t bytes) {
     return OF3D_OK;
 }
 
-// Volumes of compute type needed by the generic pipeline (see run_generic)
-static int generic_volumes(int ndim) { return ndim == 3 ? 2 + 2 + 4 + 1 + 9 : 2 + 2 + 3 + 1 + 5; }
+// Volumes of compute type needed by the generic pipeline (see GenericPipe::run_spatial), excluding ic and dt0
+static int generic_volumes(int ndim) { return ndim == 3 ? 2 + 4 + 1 + 9 : 2 + 3 + 1 + 5; }
 
-static size_t plan_bytes(int ndim, int64_t kt, int64_t n, int64_t plane, int in_dtype, int precision, int in_mem, int out_mem) {
+// Device workspace of one call.  nz planes are given, own_n of them are produced (3D ranges: z-slab sharding, slab
+// pipeline).  fast / fused say which pipeline will run (upper bound over both when unknown: fast = -1).
+static size_t plan_bytes(int ndim, int64_t kt, int64_t nz, int64_t own_n, int64_t plane, int nw, int in_dtype, int precision, int in_mem,
+                         int out_mem, int fast, bool fused, bool rel_f32) {
     const size_t ts = precision == OF3D_FP32 ? 4 : 8;
-    size_t b = 0;
-    b += (size_t)std::max(generic_volumes(ndim), 2 + fast_volumes(ndim)) * align_up((size_t)n * ts);
-    if (in_mem == OF3D_HOST) b += (size_t)kt * align_up((size_t)n * dtype_size(in_dtype));
-    if (out_mem == OF3D_HOST) b += (size_t)(ndim + 1) * align_up((size_t)n * ts);
-    if (precision == OF3D_FP64) b += align_up((size_t)n * 8);     // float64 reliability scratch of OF3D_FLAG_REL_F32
-    if (ndim == 3) b += (size_t)4 * 2 * kMaxZPad * (size_t)plane * ts + 4096;   // replicated edge planes of the gradient volumes
-    return b + 4096;
+    const size_t n = (size_t)nz * plane, vol = align_up(n * ts);
+    size_t fast_b = 0, gen_b = 0;
+    if (ndim == 3) {
+        const size_t ng = align_up((size_t)std::min<int64_t>(nz, own_n + 2 * (nw / 2)) * plane * ts);
+        fast_b = std::max(3 * ng, align_up(9 * (size_t)own_n * plane * ts)) + 4 * ng + (fused ? 0 : 2 * vol);
+    } else {
+        fast_b = 5 * vol;
+    }
+    gen_b = (size_t)(2 + generic_volumes(ndim)) * vol + (own_n != nz ? 4 * vol : 0) + (rel_f32 ? align_up(n * 8) : 0);
+    size_t b = fast < 0 ? std::max(fast_b, gen_b) : (fast ? fast_b : gen_b);
+    if (in_mem == OF3D_HOST) b += (size_t)kt * align_up(n * dtype_size(in_dtype));
+    if (out_mem == OF3D_HOST) b += (size_t)(ndim + 1) * align_up((size_t)own_n * plane * ts);
+    return b + 8192;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -211,13 +221,21 @@ static int check_taps(const of3d_taps* t) {
     return OF3D_OK;
 }
 
-// fp != nullptr: run the temporal stage on the frames into (ic_out, dt0_out) (workspace if null);
+// fp != nullptr: the temporal stage runs on the frames (into (ic_out, dt0_out) when given);
 // fp == nullptr: (ic_in, dt0_in) are given.  spatial == false stops after the temporal stage.
+// 3D: the flow of the planes [own_lo, own_lo + own_n) is written to outputs of own_n planes.
 template <typename T, bool EXACT>
 static int run_pipe(of3d_ctx* c, const Shape& s, const FramePtrs* fp, int in_dtype, const of3d_taps* t, unsigned flags,
-                    const T* ic_in, const T* dt0_in, T* ic_out, T* dt0_out, bool spatial, T* vx, T* vy, T* vz, T* rel) {
+                    const T* ic_in, const T* dt0_in, T* ic_out, T* dt0_out, bool spatial, int64_t own_lo, int64_t own_n,
+                    T* vx, T* vy, T* vz, T* rel, bool rel_f32) {
     GenericPipe<T, EXACT> g{c, s, make_filt<T>(t->D, t->nD), make_filt<T>(t->S, t->nS), make_filt<T>(t->G, t->nG),
                             make_filt<T>(t->T, t->nT), make_filt<T>(t->W, t->nW)};
+    const bool fast = !EXACT && !(flags & OF3D_FLAG_GENERIC) && fast_supported(t);
+    // marching kernels with the temporal derivative fused into the z march (kernels_tz.cuh)
+    if (fast && spatial && fp && !ic_out && s.ndim == 3 && fused_temporal_ok(t, *fp, in_dtype, s.nx) && !getenv("OF3D_NO_FUSED_T")) {
+        const int rc = run_fast<T>(c, s, fp, in_dtype, nullptr, nullptr, t, own_lo, own_n, vx, vy, vz, rel, rel_f32);
+        if (rc != kNotSupported) return rc;
+    }
     const T* ic = ic_in; const T* dt0 = dt0_in;
     if (fp) {
         T* a = ic_out ? ic_out : ws_take<T>(c, s.n());
@@ -226,32 +244,57 @@ static int run_pipe(of3d_ctx* c, const Shape& s, const FramePtrs* fp, int in_dty
         ic = a; dt0 = b;
     }
     if (!spatial) return OF3D_OK;
-    if (!EXACT && !(flags & OF3D_FLAG_GENERIC) && fast_supported(t)) {
-        const int rc = run_fast<T>(c, s, ic, dt0, t, vx, vy, vz, rel);   // marching kernels (kernels_march.cuh)
+    if (fast) {
+        const int rc = run_fast<T>(c, s, nullptr, 0, ic, dt0, t, own_lo, own_n, vx, vy, vz, rel, rel_f32);   // marching kernels
         if (rc != kNotSupported) return rc;
     }
-    return g.run_spatial(ic, dt0, vx, vy, vz, rel);
+    // generic kernels: whole volume, then the owned planes are copied out
+    const bool whole = own_lo == 0 && own_n == s.nz;
+    const int64_t plane = s.ny * s.nx;
+    T* o[4] = {vx, vy, vz, rel};
+    if (!whole) for (int i = 0; i < 4; ++i) o[i] = (i == 2 && s.ndim == 2) ? nullptr : ws_take<T>(c, s.n());
+    else if (rel_f32) o[3] = ws_take<T>(c, s.n());
+    if (int rc = g.run_spatial(ic, dt0, o[0], o[1], o[2], o[3])) return rc;
+    T* fin[4] = {vx, vy, vz, rel};
+    for (int i = 0; i < 4; ++i) {
+        if (!fin[i] || fin[i] == o[i]) continue;
+        const T* srcp = o[i] + own_lo * plane;
+        if (i == 3 && rel_f32) {
+            if constexpr (sizeof(T) == 8) {
+                StageScope span(c, OF3D_STAGE_GENERIC);           // epilogue of calc_flow.py:355-357
+                narrow_f64_f32<<<grid_for(c, own_n * plane), 256, 0, c->stream>>>(srcp, reinterpret_cast<float*>(rel), own_n * plane);
+                c->launches++;
+            }
+        } else {
+            OF3D_CUDA_TRY(cudaMemcpyAsync(fin[i], srcp, (size_t)own_n * plane * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+        }
+    }
+    return OF3D_OK;
 }
 
 template <typename T>
 static int run_typed(of3d_ctx* c, const Shape& s, const FramePtrs* fp, int in_dtype, const of3d_taps* t, unsigned flags,
-                     const void* ic_in, const void* dt0_in, void* ic_out, void* dt0_out, bool spatial, void* const dout[4]) {
+                     const void* ic_in, const void* dt0_in, void* ic_out, void* dt0_out, bool spatial, int64_t own_lo, int64_t own_n,
+                     void* const dout[4], bool rel_f32) {
     if (flags & OF3D_FLAG_EXACT)
         return run_pipe<T, true>(c, s, fp, in_dtype, t, flags, (const T*)ic_in, (const T*)dt0_in, (T*)ic_out, (T*)dt0_out, spatial,
-                                 (T*)dout[0], (T*)dout[1], (T*)dout[2], (T*)dout[3]);
+                                 own_lo, own_n, (T*)dout[0], (T*)dout[1], (T*)dout[2], (T*)dout[3], rel_f32);
     return run_pipe<T, false>(c, s, fp, in_dtype, t, flags, (const T*)ic_in, (const T*)dt0_in, (T*)ic_out, (T*)dt0_out, spatial,
-                              (T*)dout[0], (T*)dout[1], (T*)dout[2], (T*)dout[3]);
+                              own_lo, own_n, (T*)dout[0], (T*)dout[1], (T*)dout[2], (T*)dout[3], rel_f32);
 }
 
 // stage: 0 = whole operator from frames, 1 = temporal stage only (frames -> ic, dt0 device buffers),
 //        2 = spatial stages from (ic, dt0) device buffers
+// The inputs hold nz planes; in 3D the outputs hold the own_n planes [own_lo, own_lo + own_n) (own_n = 0: all of them).
 static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* frames, int in_dtype, int in_mem, int64_t nz,
                        int64_t ny, int64_t nx, const of3d_taps* t, int precision, unsigned flags, void* ic_dev, void* dt0_dev,
-                       void* vx, void* vy, void* vz, void* rel, int out_mem) {
+                       void* vx, void* vy, void* vz, void* rel, int out_mem, int64_t own_lo = 0, int64_t own_n = 0) {
     if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
     if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3"); return OF3D_ERR_ARG; }
     if (int rc = check_taps(t)) return rc;
     if (nz < 1 || ny < 1 || nx < 1 || (ndim == 2 && nz != 1)) { set_error("bad volume shape"); return OF3D_ERR_ARG; }
+    if (own_n == 0) { own_lo = 0; own_n = nz; }
+    if (own_lo < 0 || own_n < 1 || own_lo + own_n > nz) { set_error("bad z range"); return OF3D_ERR_ARG; }
     if (precision != OF3D_FP64 && precision != OF3D_FP32) { set_error("precision must be OF3D_FP64 or OF3D_FP32"); return OF3D_ERR_ARG; }
     if ((in_mem != OF3D_HOST && in_mem != OF3D_DEVICE) || (out_mem != OF3D_HOST && out_mem != OF3D_DEVICE)) { set_error("bad memory space"); return OF3D_ERR_ARG; }
     if (stage != 2) {
@@ -260,6 +303,7 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
         for (int k = 0; k < t->nT; ++k) if (!frames[k]) { set_error("null frame pointer"); return OF3D_ERR_ARG; }
     }
     if (stage != 0 && (!ic_dev || !dt0_dev)) { set_error("null ic/dt0 pointer"); return OF3D_ERR_ARG; }
+    const bool rel_f32 = stage != 1 && precision == OF3D_FP64 && (flags & OF3D_FLAG_REL_F32);
     {
         // device buffers of the compute type are accessed with 8-byte (fp64) / 4-byte (fp32) vector-free loads and
         // cp.async: they must be naturally aligned
@@ -267,8 +311,8 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
         const void* chk[6] = {stage != 0 ? ic_dev : nullptr, stage != 0 ? dt0_dev : nullptr,
                               out_mem == OF3D_DEVICE ? vx : nullptr, out_mem == OF3D_DEVICE ? vy : nullptr,
                               out_mem == OF3D_DEVICE ? vz : nullptr, out_mem == OF3D_DEVICE ? rel : nullptr};
-        if ((flags & OF3D_FLAG_REL_F32) && reinterpret_cast<uintptr_t>(rel) % 4) { set_error("device buffers must be aligned to the compute type"); return OF3D_ERR_ARG; }
-        if (flags & OF3D_FLAG_REL_F32) chk[5] = nullptr;
+        if (rel_f32 && reinterpret_cast<uintptr_t>(rel) % 4) { set_error("device buffers must be aligned to the compute type"); return OF3D_ERR_ARG; }
+        if (rel_f32) chk[5] = nullptr;
         for (const void* q : chk)
             if (q && reinterpret_cast<uintptr_t>(q) % al) { set_error("device buffers must be aligned to the compute type"); return OF3D_ERR_ARG; }
         if (stage != 2 && in_mem == OF3D_DEVICE)
@@ -279,10 +323,21 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
     OF3D_CUDA_TRY(cudaSetDevice(c->device));
 
     const Shape s{ndim, nz, ny, nx};
-    const int64_t n = s.n();
+    const int64_t n = s.n(), n_own = own_n * ny * nx;
     const size_t ts = precision == OF3D_FP32 ? 4 : 8;
-    if (int rc = ws_ensure(c, plan_bytes(ndim, stage == 2 ? 0 : t->nT, n, ny * nx, in_dtype, precision, stage == 2 ? OF3D_DEVICE : in_mem,
-                                         stage == 1 ? OF3D_DEVICE : out_mem))) return rc;
+    {
+        const bool fast = !(flags & (OF3D_FLAG_EXACT | OF3D_FLAG_GENERIC)) && fast_supported(t);
+        // (host frames are staged 512-byte aligned, device frames are checked again where the kernel is chosen)
+        bool fused = fast && stage == 0 && ndim == 3 && !getenv("OF3D_NO_FUSED_T");
+        if (fused) {
+            FramePtrs probe;
+            memset(&probe, 0, sizeof(probe));
+            if (in_mem == OF3D_DEVICE) for (int k = 0; k < t->nT; ++k) probe.p[k] = frames[k];
+            fused = fused_temporal_ok(t, probe, in_dtype, nx);
+        }
+        if (int rc = ws_ensure(c, plan_bytes(ndim, stage == 2 ? 0 : t->nT, nz, own_n, ny * nx, t->nW, in_dtype, precision,
+                                             stage == 2 ? OF3D_DEVICE : in_mem, stage == 1 ? OF3D_DEVICE : out_mem, fast ? 1 : 0, fused, rel_f32))) return rc;
+    }
     c->ws_off = 0;
 
     FramePtrs fp;
@@ -305,31 +360,21 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
     const int oidx3[4] = {0, 1, 2, 3}, oidx2[3] = {0, 1, 3};
     const int* oidx = ndim == 3 ? oidx3 : oidx2;
     if (stage != 1 && out_mem == OF3D_HOST)
-        for (int i = 0; i < nout; ++i) dout[oidx[i]] = ws_take<char>(c, (size_t)n * ts);
-    // OF3D_FLAG_REL_F32: the kernels write the float64 reliability to scratch; one narrowing pass fills the float32 buffer
-    const bool narrow = stage != 1 && precision == OF3D_FP64 && (flags & OF3D_FLAG_REL_F32);
-    void* rel_f32 = dout[3];
-    if (narrow) dout[3] = ws_take<char>(c, (size_t)n * 8);
+        for (int i = 0; i < nout; ++i) dout[oidx[i]] = ws_take<char>(c, (size_t)n_own * ts);
 
     const FramePtrs* fpp = stage == 2 ? nullptr : &fp;
     int rc;
     if (precision == OF3D_FP64)
         rc = run_typed<double>(c, s, fpp, in_dtype, t, flags, ic_dev, dt0_dev, stage == 1 ? ic_dev : nullptr,
-                               stage == 1 ? dt0_dev : nullptr, stage != 1, dout);
+                               stage == 1 ? dt0_dev : nullptr, stage != 1, own_lo, own_n, dout, rel_f32);
     else
         rc = run_typed<float>(c, s, fpp, in_dtype, t, flags, ic_dev, dt0_dev, stage == 1 ? ic_dev : nullptr,
-                              stage == 1 ? dt0_dev : nullptr, stage != 1, dout);
+                              stage == 1 ? dt0_dev : nullptr, stage != 1, own_lo, own_n, dout, false);
     if (rc) return rc;
-    if (narrow) {
-        StageScope span(c, OF3D_STAGE_WINDOW_XY_SOLVE);           // epilogue of calc_flow.py:355-357
-        narrow_f64_f32<<<grid_for(c, n), 256, 0, c->stream>>>((const double*)dout[3], (float*)rel_f32, n);
-        c->launches++;
-        dout[3] = rel_f32;
-    }
     OF3D_CUDA_TRY(cudaGetLastError());
     if (stage != 1 && out_mem == OF3D_HOST)
         for (int i = 0; i < nout; ++i)
-            OF3D_CUDA_TRY(cudaMemcpyAsync(out[oidx[i]], dout[oidx[i]], (size_t)n * ((narrow && oidx[i] == 3) ? 4 : ts),
+            OF3D_CUDA_TRY(cudaMemcpyAsync(out[oidx[i]], dout[oidx[i]], (size_t)n_own * ((rel_f32 && oidx[i] == 3) ? 4 : ts),
                                           cudaMemcpyDeviceToHost, c->stream));
     const bool all_device = (stage == 2 || in_mem == OF3D_DEVICE) && (stage == 1 || out_mem == OF3D_DEVICE);
     if (!(c->async && all_device)) OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -424,8 +469,9 @@ OF3D_API int of3d_create(int device, of3d_ctx** out) {
     c->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
-    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; set_error(std::string("cudaStreamCreate failed: ") + cudaGetErrorString(e)); return OF3D_ERR_CUDA; }
+    c->stream = c->own_stream;
     *out = c;
     return OF3D_OK;
 }
@@ -433,7 +479,12 @@ OF3D_API int of3d_create(int device, of3d_ctx** out) {
 OF3D_API int of3d_destroy(of3d_ctx* c) {
     if (!c) return OF3D_OK;
     cudaSetDevice(c->device);
-    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) of3d_comm_destroy(c);
+    if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
+    if (c->s_comm) cudaStreamDestroy(c->s_comm);
+    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->ws) cudaFree(c->ws);
@@ -453,7 +504,7 @@ OF3D_API int of3d_destroy(of3d_ctx* c) {
 OF3D_API size_t of3d_workspace_bytes(int ndim, int64_t nt_taps, int64_t nz, int64_t ny, int64_t nx, int in_dtype, int precision,
                             int in_mem, int out_mem) {
     if (ndim != 2 && ndim != 3) return 0;
-    return plan_bytes(ndim, nt_taps, nz * ny * nx, ny * nx, in_dtype, precision, in_mem, out_mem);
+    return plan_bytes(ndim, nt_taps, nz, nz, ny * nx, 0, in_dtype, precision, in_mem, out_mem, -1, false, true);
 }
 
 OF3D_API int of3d_reserve(of3d_ctx* c, size_t bytes) {
@@ -526,18 +577,18 @@ OF3D_API int of3d_window_upload(of3d_ctx* c, int k, int n_frames, const void* ho
 }
 
 // The synchronous host call in z slabs: while slab s is copied back, slab s + 1 is computed and the planes of later
-// slabs are still arriving.  A slab is computed on its extension by H = R_gradient + R_window planes (the z support of
-// the operator), of which only the interior is returned: bit-identical to the whole-volume run.
+// slabs are still arriving.  A slab is computed from its extension by H = R_gradient + R_window planes (the z support of
+// the operator) with the owned-range pipeline, which returns the interior only: bit-identical to the whole-volume run.
 static int window_flow_pipelined(of3d_ctx* c, int in_dtype, int64_t nz, int64_t ny, int64_t nx, const of3d_taps* t, int precision,
                                  unsigned flags, void* const hout[4], int64_t slab) {
-    const int64_t plane = ny * nx, n = nz * plane;
+    const int64_t plane = ny * nx;
     const size_t ts = precision == OF3D_FP32 ? 4 : 8, ib = dtype_size(in_dtype);
     const int64_t H = std::max(std::max(t->nD, t->nG), t->nS) / 2 + t->nW / 2;
     const int64_t ext_max = std::min(nz, slab + 2 * H);
     const size_t osz[4] = {ts, ts, ts, (precision == OF3D_FP64 && (flags & OF3D_FLAG_REL_F32)) ? (size_t)4 : ts};
-    // device buffers: ic, dt0, two sets of four extended-slab outputs
-    const size_t vol_b = align_up((size_t)n * ts), ext_b = align_up((size_t)ext_max * plane * 8);
-    const size_t need = 2 * vol_b + 8 * ext_b;
+    // device buffers: two sets of four slab outputs
+    const size_t out_b = align_up((size_t)slab * plane * 8);
+    const size_t need = 8 * out_b;
     if (c->pipe_cap < need) {
         OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
         OF3D_CUDA_TRY(cudaStreamSynchronize(c->s_dn));
@@ -548,16 +599,15 @@ static int window_flow_pipelined(of3d_ctx* c, int in_dtype, int64_t nz, int64_t 
         c->pipe_cap = need;
     }
     // one arena size for every stage call of the pipeline (no re-allocation in flight)
-    if (int rc = ws_ensure(c, plan_bytes(3, 0, ext_max * plane, plane, in_dtype, precision, OF3D_DEVICE, OF3D_DEVICE))) return rc;
-    char* ic = c->pipe; char* dt0 = c->pipe + vol_b;
+    if (int rc = ws_ensure(c, plan_bytes(3, t->nT, ext_max, std::min(slab, nz), plane, t->nW, in_dtype, precision, OF3D_DEVICE, OF3D_DEVICE, -1, false, true))) return rc;
     char* ext[2][4];
-    for (int q = 0; q < 2; ++q) for (int i = 0; i < 4; ++i) ext[q][i] = c->pipe + 2 * vol_b + (size_t)(q * 4 + i) * ext_b;
+    for (int q = 0; q < 2; ++q) for (int i = 0; i < 4; ++i) ext[q][i] = c->pipe + (size_t)(q * 4 + i) * out_b;
     const size_t slot = align_up(c->win_frame);
     const int saved_async = c->async;
     c->async = 1;                                               // the stage calls below must not synchronise
     // (a lambda so that every early error return still restores the context and drains the streams below)
     auto run = [&]() -> int {
-        int64_t tz = 0;                                         // planes whose temporal stage has been enqueued
+        int64_t tz = 0;                                         // planes whose arrival the compute stream already waits for
         int ns = 0;
         for (int64_t a = 0; a < nz; a += slab, ++ns) {
             const int64_t b = std::min(nz, a + slab), a2 = std::max<int64_t>(0, a - H), b2 = std::min(nz, b + H);
@@ -567,23 +617,19 @@ static int window_flow_pipelined(of3d_ctx* c, int in_dtype, int64_t nz, int64_t 
                 cudaEvent_t ev = nullptr;
                 for (const auto& pt : c->parts) if (pt.off < limit) ev = pt.ev;
                 if (ev) OF3D_CUDA_TRY(cudaStreamWaitEvent(c->stream, ev, 0));
-                const void* frames[kMaxFrames];
-                for (int k = 0; k < t->nT; ++k) frames[k] = c->win + (size_t)k * slot + (size_t)tz * plane * ib;
-                if (int rc = flow_staged(c, 1, 3, frames, in_dtype, OF3D_DEVICE, b2 - tz, ny, nx, t, precision, flags,
-                                         ic + (size_t)tz * plane * ts, dt0 + (size_t)tz * plane * ts, nullptr, nullptr, nullptr, nullptr,
-                                         OF3D_DEVICE)) return rc;
                 tz = b2;
             }
             const int q = ns & 1;
             if (ns >= 2) OF3D_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_dn[q], 0));   // the copy-back of slab ns - 2 has left the buffers
-            if (int rc = flow_staged(c, 2, 3, nullptr, in_dtype, OF3D_DEVICE, b2 - a2, ny, nx, t, precision, flags,
-                                     ic + (size_t)a2 * plane * ts, dt0 + (size_t)a2 * plane * ts, ext[q][0], ext[q][1], ext[q][2], ext[q][3],
-                                     OF3D_DEVICE)) return rc;
+            const void* frames[kMaxFrames];
+            for (int k = 0; k < t->nT; ++k) frames[k] = c->win + (size_t)k * slot + (size_t)a2 * plane * ib;
+            if (int rc = flow_staged(c, 0, 3, frames, in_dtype, OF3D_DEVICE, b2 - a2, ny, nx, t, precision, flags, nullptr, nullptr,
+                                     ext[q][0], ext[q][1], ext[q][2], ext[q][3], OF3D_DEVICE, a - a2, b - a)) return rc;
             OF3D_CUDA_TRY(cudaEventRecord(c->ev_c, c->stream));
             OF3D_CUDA_TRY(cudaStreamWaitEvent(c->s_dn, c->ev_c, 0));
             for (int i = 0; i < 4; ++i)
-                OF3D_CUDA_TRY(cudaMemcpyAsync((char*)hout[i] + (size_t)a * plane * osz[i], ext[q][i] + (size_t)(a - a2) * plane * osz[i],
-                                              (size_t)(b - a) * plane * osz[i], cudaMemcpyDeviceToHost, c->s_dn));
+                OF3D_CUDA_TRY(cudaMemcpyAsync((char*)hout[i] + (size_t)a * plane * osz[i], ext[q][i], (size_t)(b - a) * plane * osz[i],
+                                              cudaMemcpyDeviceToHost, c->s_dn));
             OF3D_CUDA_TRY(cudaEventRecord(c->ev_dn[q], c->s_dn));
         }
         return OF3D_OK;
@@ -634,6 +680,14 @@ OF3D_API int of3d_flow_from_dt(of3d_ctx* ctx, int ndim, const void* ic_dev, cons
 }
 
 OF3D_API void* of3d_stream(of3d_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+OF3D_API int of3d_set_stream(of3d_ctx* c, void* cuda_stream) {
+    if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));            // nothing of the context is left behind on the old stream
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return OF3D_OK;
+}
 
 OF3D_API int of3d_set_async(of3d_ctx* c, int enable) {
     if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
@@ -730,6 +784,247 @@ OF3D_API int of3d_mask_derive(of3d_ctx* c, const void* vx, const void* vy, const
     OF3D_CUDA_TRY(cudaGetLastError());
     OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return OF3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// z-slab sharding.  NCCL is bound at run time (dlopen): a process that never shards needs no NCCL, and a
+// process that already holds one (PyTorch) shares it.
+namespace {
+struct NcclId { char b[128]; };                                  // ncclUniqueId
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl() {
+    static NcclApi api = [] {
+        NcclApi a;
+        a.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.h) a.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.h) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
+        a.Send = (decltype(a.Send))dlsym(a.h, "ncclSend");
+        a.Recv = (decltype(a.Recv))dlsym(a.h, "ncclRecv");
+        a.GroupStart = (decltype(a.GroupStart))dlsym(a.h, "ncclGroupStart");
+        a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.h, "ncclGroupEnd");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.GroupStart && a.GroupEnd;
+        return a;
+    }();
+    return api;
+}
+int nccl_fail(const char* what, int r) {
+    NcclApi& n = nccl();
+    set_error(std::string(what) + " failed: " + ((n.GetErrorString && r) ? n.GetErrorString(r) : "NCCL is not available (libnccl.so.2 not found)"));
+    return OF3D_ERR_CUDA;
+}
+constexpr int kNcclUint8 = 1;                                    // ncclUint8
+}  // namespace
+
+OF3D_API int of3d_comm_unique_id(void* id128) {
+    if (!id128) { set_error("id is null"); return OF3D_ERR_ARG; }
+    NcclApi& n = nccl();
+    if (!n.ok) return nccl_fail("loading NCCL", 0);
+    NcclId id;
+    if (int r = n.GetUniqueId(&id)) return nccl_fail("ncclGetUniqueId", r);
+    memcpy(id128, &id, sizeof(id));
+    return OF3D_OK;
+}
+
+OF3D_API int of3d_comm_init(of3d_ctx* c, const void* id128, int nranks, int rank) {
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_error("bad argument"); return OF3D_ERR_ARG; }
+    NcclApi& n = nccl();
+    if (!n.ok) return nccl_fail("loading NCCL", 0);
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    if (c->comm) of3d_comm_destroy(c);
+    NcclId id;
+    memcpy(&id, id128, sizeof(id));
+    if (int r = n.CommInitRank(&c->comm, nranks, id, rank)) { c->comm = nullptr; return nccl_fail("ncclCommInitRank", r); }
+    c->comm_rank = rank; c->comm_size = nranks;
+    if (!c->s_comm) {
+        OF3D_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
+        OF3D_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+        OF3D_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    }
+    return OF3D_OK;
+}
+
+OF3D_API int of3d_comm_destroy(of3d_ctx* c) {
+    if (!c || !c->comm) return OF3D_OK;
+    cudaSetDevice(c->device);
+    if (c->s_comm) cudaStreamSynchronize(c->s_comm);
+    nccl().CommDestroy(c->comm);
+    c->comm = nullptr; c->comm_size = 1; c->comm_rank = 0; c->halo_pending = false;
+    return OF3D_OK;
+}
+
+OF3D_API int of3d_halo_exchange(of3d_ctx* c, void* const* frames_ext, int n_frames, size_t plane_bytes, int64_t lo, int64_t own,
+                                int64_t hi, int64_t send_dn, int64_t send_up) {
+    if (!c || !frames_ext || n_frames < 1 || plane_bytes == 0 || lo < 0 || hi < 0 || own < 1 || send_dn < 0 || send_up < 0 ||
+        send_dn > own || send_up > own) { set_error("bad argument"); return OF3D_ERR_ARG; }
+    if (!c->comm) { set_error("of3d_halo_exchange: no communicator (of3d_comm_init)"); return OF3D_ERR_ARG; }
+    for (int k = 0; k < n_frames; ++k) if (!frames_ext[k]) { set_error("null frame pointer"); return OF3D_ERR_ARG; }
+    NcclApi& n = nccl();
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    const int r = c->comm_rank, last = c->comm_size - 1;
+    // the owned planes may still be written by work queued on the compute stream
+    OF3D_CUDA_TRY(cudaEventRecord(c->ev_ready, c->stream));
+    OF3D_CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_ready, 0));
+    if (int e = n.GroupStart()) return nccl_fail("ncclGroupStart", e);
+    int err = 0;
+    for (int k = 0; k < n_frames && !err; ++k) {
+        char* f = static_cast<char*>(frames_ext[k]);
+        if (r > 0) {
+            if (send_dn && !err) err = n.Send(f + (size_t)lo * plane_bytes, (size_t)send_dn * plane_bytes, kNcclUint8, r - 1, c->comm, c->s_comm);
+            if (lo && !err) err = n.Recv(f, (size_t)lo * plane_bytes, kNcclUint8, r - 1, c->comm, c->s_comm);
+        }
+        if (r < last) {
+            if (send_up && !err) err = n.Send(f + (size_t)(lo + own - send_up) * plane_bytes, (size_t)send_up * plane_bytes, kNcclUint8, r + 1, c->comm, c->s_comm);
+            if (hi && !err) err = n.Recv(f + (size_t)(lo + own) * plane_bytes, (size_t)hi * plane_bytes, kNcclUint8, r + 1, c->comm, c->s_comm);
+        }
+    }
+    const int e2 = n.GroupEnd();
+    if (err) return nccl_fail("ncclSend/ncclRecv", err);
+    if (e2) return nccl_fail("ncclGroupEnd", e2);
+    OF3D_CUDA_TRY(cudaEventRecord(c->ev_halo, c->s_comm));
+    c->halo_pending = true;
+    return OF3D_OK;
+}
+
+OF3D_API int of3d_flow3d_slab(of3d_ctx* c, const void* const* frames_ext, int in_dtype, int64_t nz_ext, int64_t ny, int64_t nx,
+                              int64_t own_lo, int64_t own_n, int64_t chunk_planes, const of3d_taps* t, int precision, unsigned flags,
+                              void* vx, void* vy, void* vz, void* rel) {
+    if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
+    if (int rc = check_taps(t)) return rc;
+    if (nz_ext < 1 || own_lo < 0 || own_n < 1 || own_lo + own_n > nz_ext || chunk_planes < 0) { set_error("bad z range"); return OF3D_ERR_ARG; }
+    if (!frames_ext || !vx || !vy || !vz || !rel) { set_error("null image or output pointer"); return OF3D_ERR_ARG; }
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    const int64_t plane = ny * nx;
+    const int64_t H = std::max(std::max(t->nD, t->nG), t->nS) / 2 + t->nW / 2;
+    const size_t ts = precision == OF3D_FP32 ? 4 : 8, ib = dtype_size(in_dtype);
+    const size_t rs = (precision == OF3D_FP64 && (flags & OF3D_FLAG_REL_F32)) ? 4 : ts;
+    if (!ib) { set_error("unsupported input dtype"); return OF3D_ERR_ARG; }
+    const int64_t chunk = chunk_planes ? std::min(chunk_planes, own_n) : own_n;
+    // chunks whose z support lies inside the owned planes run first: they overlap the halo exchange in flight
+    std::vector<int64_t> starts, late;
+    for (int64_t a = own_lo; a < own_lo + own_n; a += chunk) {
+        const int64_t b = std::min(own_lo + own_n, a + chunk);
+        const bool interior = a - H >= own_lo && b + H <= own_lo + own_n;
+        (c->halo_pending && !interior ? late : starts).push_back(a);
+    }
+    const size_t n_first = starts.size();
+    starts.insert(starts.end(), late.begin(), late.end());
+    // one arena size for every chunk (no re-allocation while kernels are queued)
+    {
+        const int64_t ext_max = std::min(nz_ext, chunk + 2 * H);
+        if (int rc = ws_ensure(c, plan_bytes(3, t->nT, ext_max, chunk, plane, t->nW, in_dtype, precision, OF3D_DEVICE, OF3D_DEVICE, -1, false, true))) return rc;
+    }
+    const int saved_async = c->async;
+    c->async = 1;
+    int rc = OF3D_OK;
+    for (size_t i = 0; i < starts.size() && !rc; ++i) {
+        if (i == n_first && c->halo_pending) {
+            cudaError_t e = cudaStreamWaitEvent(c->stream, c->ev_halo, 0);
+            if (e != cudaSuccess) { set_error(std::string("cudaStreamWaitEvent failed: ") + cudaGetErrorString(e)); rc = OF3D_ERR_CUDA; break; }
+            c->halo_pending = false;
+        }
+        const int64_t a = starts[i], b = std::min(own_lo + own_n, a + chunk);
+        const int64_t a2 = std::max<int64_t>(0, a - H), b2 = std::min(nz_ext, b + H);
+        const void* frames[kMaxFrames];
+        for (int k = 0; k < t->nT; ++k) {
+            if (!frames_ext[k]) { set_error("null frame pointer"); rc = OF3D_ERR_ARG; break; }
+            frames[k] = static_cast<const char*>(frames_ext[k]) + (size_t)a2 * plane * ib;
+        }
+        if (rc) break;
+        const size_t o = (size_t)(a - own_lo) * plane;
+        rc = flow_staged(c, 0, 3, frames, in_dtype, OF3D_DEVICE, b2 - a2, ny, nx, t, precision, flags, nullptr, nullptr,
+                         (char*)vx + o * ts, (char*)vy + o * ts, (char*)vz + o * ts, (char*)rel + o * rs, OF3D_DEVICE, a - a2, b - a);
+    }
+    if (c->halo_pending) { cudaStreamWaitEvent(c->stream, c->ev_halo, 0); c->halo_pending = false; }   // later calls see the halo too
+    c->async = saved_async;
+    if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+    if (!c->async) OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return OF3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TIFF strip decoders (host code; SURVEY.md 8(f) rank 2: the MATLAB twin writes LZW, src/MATLAB/TIFFwrite.m:27).
+namespace {
+// TIFF 6.0 LZW: MSB-first codes of 9..12 bits, ClearCode 256, EOI 257, the code width grows one code early.
+int64_t lzw_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
+    struct Entry { uint32_t prev; uint32_t len; uint8_t first, last; };
+    static thread_local std::vector<Entry> tab(4096);
+    for (int i = 0; i < 256; ++i) tab[i] = {0xffffffffu, 1, (uint8_t)i, (uint8_t)i};
+    uint32_t next = 258, nbits = 9, acc = 0, have = 0;
+    int64_t prev = -1;
+    size_t in = 0, out = 0;
+    bool cleared = false;
+    while (out < cap) {
+        while (have < nbits) {
+            if (in >= n) return (int64_t)out;
+            acc = (acc << 8) | src[in++];
+            have += 8;
+        }
+        const uint32_t code = (acc >> (have - nbits)) & ((1u << nbits) - 1u);
+        have -= nbits;
+        if (code == 257) break;
+        if (code == 256) { next = 258; nbits = 9; prev = -1; cleared = true; continue; }
+        if (!cleared) return -1;
+        uint32_t emit = code;
+        if (prev >= 0) {
+            if (code > next || (code == next && next >= 4096)) return -1;
+            // new entry = prev + first(code); for code == next (KwKwK) that is prev + first(prev)
+            if (next < 4096) tab[next] = {(uint32_t)prev, tab[prev].len + 1, tab[prev].first, code == next ? tab[prev].first : tab[code].first};
+            if (next < 4096) ++next;
+            if (next + 1 >= (1u << nbits) && nbits < 12) ++nbits;
+        } else if (code >= 256) return -1;
+        // write the string of `emit` back to front
+        const uint32_t len = tab[emit].len;
+        size_t end = out + len;
+        uint32_t e = emit;
+        for (size_t p = end; p-- > out;) {
+            if (p < cap) dst[p] = tab[e].last;
+            e = tab[e].prev;
+        }
+        out = end < cap ? end : cap;
+        prev = code;
+    }
+    return (int64_t)out;
+}
+
+int64_t packbits_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
+    size_t in = 0, out = 0;
+    while (in < n && out < cap) {
+        const int h = (int8_t)src[in++];
+        if (h >= 0) {
+            size_t cnt = (size_t)h + 1;
+            if (in + cnt > n) cnt = n - in;
+            for (size_t i = 0; i < cnt && out < cap; ++i) dst[out++] = src[in + i];
+            in += cnt;
+        } else if (h != -128) {
+            if (in >= n) break;
+            const uint8_t v = src[in++];
+            for (int i = 0; i < 1 - h && out < cap; ++i) dst[out++] = v;
+        }
+    }
+    return (int64_t)out;
+}
+}  // namespace
+
+OF3D_API int64_t of3d_tiff_decode(int kind, const void* src, size_t n, void* dst, size_t cap) {
+    if ((!src && n) || (!dst && cap)) return -1;
+    if (kind == 0) return lzw_decode((const uint8_t*)src, n, (uint8_t*)dst, cap);
+    if (kind == 1) return packbits_decode((const uint8_t*)src, n, (uint8_t*)dst, cap);
+    return -1;
 }
 
 OF3D_API int of3d_synth_blobs(of3d_ctx* c, void* dev_out_u16, int64_t nt, int64_t nz, int64_t ny, int64_t nx, int64_t t0, int64_t z0,

@@ -13,14 +13,17 @@ the reference's analysis scripts rely on, with the same call names:
                                                    (ImageJ hyperstacks, including the > 4 GB single-IFD kind)
     TiffFile(path).pages[i].shape / .imagej_metadata
 
-Supported on the read side: classic TIFF and BigTIFF, both byte orders, uncompressed strips
-(Compression = 1), 8/16/32/64-bit unsigned, signed and IEEE samples, one sample per pixel.
+Supported on the read side: classic TIFF and BigTIFF, both byte orders, strips and tiles, uncompressed
+(Compression = 1), LZW (5: what the MATLAB twin writes, src/MATLAB/TIFFwrite.m:27), Deflate (8 / 32946) and PackBits
+(32773) with the horizontal (2) and floating-point (3) predictors, 8/16/32/64-bit unsigned, signed and IEEE samples,
+one sample per pixel.  The LZW and PackBits decoders are native (libof3d.so, host code); zlib is Python's.
 """
 from __future__ import annotations
 
 import json
 import os
 import struct
+import zlib
 
 import numpy as np
 
@@ -134,6 +137,98 @@ def imwrite(path, data, photometric='minisblack', bigtiff=None, description=None
 
 
 # ------------------------------------------------------------------------------------------ reader
+def lzw_decode_py(data, expected):
+    """TIFF LZW (MSB-first codes, 9-12 bits, early change, ClearCode 256, EOI 257) -> bytes.  Reference implementation in
+    pure Python: the reader uses the native decoder of libof3d.so and falls back to this one only when the library is
+    absent; the tests compare the two."""
+    out = bytearray()
+    table = None
+    nbits, nxt, prev = 9, 258, None
+    acc = bits = 0
+    it = iter(data)
+    while len(out) < expected:
+        while bits < nbits:
+            try:
+                acc = (acc << 8) | next(it)
+            except StopIteration:
+                return bytes(out)
+            bits += 8
+        code = (acc >> (bits - nbits)) & ((1 << nbits) - 1)
+        bits -= nbits
+        if code == 257:
+            break
+        if code == 256:
+            table = [bytes((i,)) for i in range(256)] + [b'', b'']
+            nbits, nxt, prev = 9, 258, None
+            continue
+        if table is None:
+            raise ValueError('tiffio: LZW stream does not start with a clear code')
+        if prev is None:
+            entry = table[code]
+        else:
+            if code < len(table):
+                entry = table[code]
+            elif code == len(table):
+                entry = prev + prev[:1]
+            else:
+                raise ValueError('tiffio: corrupt LZW stream')
+            table.append(prev + entry[:1])
+            nxt += 1
+            if nxt + 1 >= (1 << nbits) and nbits < 12:      # early change
+                nbits += 1
+        out += entry
+        prev = entry
+    return bytes(out[:expected])
+
+
+def packbits_decode_py(data, expected):
+    out = bytearray()
+    i, n = 0, len(data)
+    while i < n and len(out) < expected:
+        h = data[i]; i += 1
+        if h < 128:
+            out += data[i:i + h + 1]; i += h + 1
+        elif h > 128:
+            out += data[i:i + 1] * (257 - h); i += 1
+    return bytes(out[:expected])
+
+
+def _native_decode(kind, data, expected):
+    """LZW (kind 0) / PackBits (kind 1) through libof3d.so; None when the library cannot be loaded."""
+    try:
+        from . import _lib
+        lib = _lib.load()
+    except Exception:
+        return None
+    import ctypes as C
+    dst = np.empty(expected, dtype=np.uint8)
+    src = np.frombuffer(data, dtype=np.uint8)
+    n = lib.of3d_tiff_decode(kind, src.ctypes.data_as(C.c_void_p), src.size, dst.ctypes.data_as(C.c_void_p), expected)
+    if n < 0:
+        raise ValueError('tiffio: corrupt %s stream' % ('LZW' if kind == 0 else 'PackBits'))
+    if n < expected:
+        dst[n:] = 0
+    return dst
+
+
+def _decompress(compression, data, expected):
+    """One strip / tile -> uint8 array of `expected` bytes (short streams are zero-padded like libtiff does)."""
+    if compression == 1:
+        buf = np.frombuffer(data, dtype=np.uint8)
+    elif compression in (8, 32946):
+        buf = np.frombuffer(zlib.decompress(data), dtype=np.uint8)
+    elif compression in (5, 32773):
+        buf = _native_decode(0 if compression == 5 else 1, data, expected)
+        if buf is None:
+            raw = (lzw_decode_py if compression == 5 else packbits_decode_py)(data, expected)
+            buf = np.frombuffer(raw, dtype=np.uint8)
+    else:
+        raise NotImplementedError('tiffio: TIFF Compression=%d is not supported (supported: none, LZW, Deflate, PackBits)' % compression)
+    if buf.size < expected:
+        buf = np.concatenate([buf, np.zeros(expected - buf.size, np.uint8)])
+    return buf[:expected]
+
+
 class TiffPage:
     def __init__(self, tags, byteorder):
         self.tags = tags
@@ -146,15 +241,28 @@ class TiffPage:
             raise NotImplementedError('tiffio: only whole-byte single-sample images are supported')
         self.dtype = np.dtype(byteorder + kind + str(bits // 8))
         self.compression = int(tags.get(259, (1,))[0])
-        self.offsets = [int(v) for v in tags[273]]
-        self.bytecounts = [int(v) for v in tags.get(279, (self.shape[0] * self.shape[1] * self.dtype.itemsize,))]
+        self.predictor = int(tags.get(317, (1,))[0])
+        self.tiled = 324 in tags
+        if self.tiled:
+            self.tile = (int(tags[323][0]), int(tags[322][0]))          # (TileLength, TileWidth)
+            self.offsets = [int(v) for v in tags[324]]
+            self.bytecounts = [int(v) for v in tags[325]]
+        else:
+            self.offsets = [int(v) for v in tags[273]]
+            self.bytecounts = [int(v) for v in tags.get(279, (self.shape[0] * self.shape[1] * self.dtype.itemsize,))]
+        self.rows_per_strip = min(int(tags.get(278, (self.shape[0],))[0]), self.shape[0])
         d = tags.get(270)
         self.description = d if isinstance(d, str) else None
 
     @property
+    def is_plain(self):
+        """uncompressed strips without a predictor: the pixel bytes can be read (or mapped) as they lie in the file"""
+        return self.compression == 1 and self.predictor == 1 and not self.tiled
+
+    @property
     def is_contiguous(self):
         o = self.offsets
-        return all(o[i] + self.bytecounts[i] == o[i + 1] for i in range(len(o) - 1))
+        return self.is_plain and all(o[i] + self.bytecounts[i] == o[i + 1] for i in range(len(o) - 1))
 
     def runs(self):
         """(file offset, byte count) of the strips, adjacent strips merged"""
@@ -171,17 +279,62 @@ class TiffPage:
             pos += cnt
         return out
 
+    def _unpredict(self, block):
+        """block: (rows, cols) view of the decoded bytes in FILE byte order, modified in place / returned"""
+        if self.predictor == 1:
+            return block
+        if self.predictor == 2:                                      # horizontal differencing, per sample, modular
+            u = block.view(self.dtype.newbyteorder(self.byteorder)).view(np.dtype(self.byteorder + 'u' + str(self.dtype.itemsize)))
+            np.cumsum(u, axis=1, dtype=u.dtype, out=u)
+            return block
+        if self.predictor == 3:                                      # floating point: bytes de-interleaved, MSB plane first
+            rows, rowbytes = block.shape
+            isz = self.dtype.itemsize
+            cols = rowbytes // isz
+            b = np.cumsum(block, axis=1, dtype=np.uint8)
+            planes = b.reshape(rows, isz, cols)                      # plane 0 = most significant byte
+            order = range(isz) if self.byteorder == '>' else range(isz - 1, -1, -1)
+            out = np.empty((rows, cols, isz), np.uint8)
+            for dst_i, src_i in enumerate(order):
+                out[:, :, dst_i] = planes[:, src_i, :]
+            block[...] = out.reshape(rows, rowbytes)
+            return block
+        raise NotImplementedError('tiffio: TIFF Predictor=%d is not supported' % self.predictor)
+
     def readinto(self, fh, dst):
         """Read the page straight into `dst`, a writable C-contiguous array of the page's shape and (file) dtype."""
-        if self.compression != 1:
-            raise NotImplementedError('tiffio: compressed TIFF (Compression=%d) is not supported' % self.compression)
-        mv = memoryview(dst).cast('B')
-        pos = 0
-        for off, cnt in self.runs():
+        if self.is_plain:
+            mv = memoryview(dst).cast('B')
+            pos = 0
+            for off, cnt in self.runs():
+                fh.seek(off)
+                if fh.readinto(mv[pos:pos + cnt]) != cnt:
+                    raise ValueError('tiffio: truncated image data')
+                pos += cnt
+            return
+        ny, nx = self.shape
+        isz = self.dtype.itemsize
+        raw = np.asarray(dst).view(np.uint8).reshape(ny, nx * isz)
+        if self.tiled:
+            th, tw = self.tile
+            across = (nx + tw - 1) // tw
+            for i, (off, cnt) in enumerate(zip(self.offsets, self.bytecounts)):
+                fh.seek(off)
+                blk = self._unpredict(_decompress(self.compression, fh.read(cnt), th * tw * isz).copy().reshape(th, tw * isz))
+                y0, x0 = (i // across) * th, (i % across) * tw
+                h, w = min(th, ny - y0), min(tw, nx - x0)
+                if h > 0 and w > 0:
+                    raw[y0:y0 + h, x0 * isz:(x0 + w) * isz] = blk[:h, :w * isz]
+            return
+        rps = self.rows_per_strip
+        for i, (off, cnt) in enumerate(zip(self.offsets, self.bytecounts)):
+            y0 = i * rps
+            if y0 >= ny:
+                break
+            h = min(rps, ny - y0)
             fh.seek(off)
-            if fh.readinto(mv[pos:pos + cnt]) != cnt:
-                raise ValueError('tiffio: truncated image data')
-            pos += cnt
+            blk = _decompress(self.compression, fh.read(cnt), h * nx * isz).copy().reshape(h, nx * isz)
+            raw[y0:y0 + h] = self._unpredict(blk)
 
     def asarray(self, fh):
         a = np.empty(self.shape, dtype=self.dtype)
@@ -215,7 +368,7 @@ class TiffFile:
             while off and off not in seen:
                 seen.add(off)
                 tags, off = self._read_ifd(fh, off)
-                if 256 in tags and 257 in tags and 273 in tags:
+                if 256 in tags and 257 in tags and (273 in tags or 324 in tags):
                     self.pages.append(TiffPage(tags, bo))
         self.imagej_metadata = self._imagej()
 
@@ -329,8 +482,8 @@ def memmap(path, mode='r'):
     tf = TiffFile(path)
     n, shape = tf.series_shape()
     p0 = tf.pages[0]
-    if p0.compression != 1:
-        raise ValueError('tiffio.memmap: compressed TIFF cannot be memory-mapped')
+    if not p0.is_plain:
+        raise ValueError('tiffio.memmap: compressed, predicted or tiled TIFF cannot be memory-mapped')
     plane = p0.shape[0] * p0.shape[1] * p0.dtype.itemsize
     if n <= len(tf.pages):
         for i, p in enumerate(tf.pages[:n]):

@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.of3d_version() == 100
+    assert lib.of3d_version() == 200
 
 
 def test_no_cpu_fallback_without_device():
