@@ -45,6 +45,37 @@ WORKLOADS = {
 }
 METRIC = 'output voxels/s (vx,vy,vz,rel) 1024x1024x128 stack'
 UNIT = 'voxels/s'
+METRICS = {
+    'cfg1': 'output voxels/s (vx,vy,vz,rel) 128x128x32 volume, 7 timepoints',
+    'cfg2': 'output pixels/s (vx,vy,rel) 2048x2048 frame time-lapse (calc_flow2D)',
+    'cfg3': 'output voxels/s (vx,vy,vz,rel) 512x512x64 stack, 31 timepoints',
+    'cfg4': METRIC,
+    'cfg5': 'output voxels/s (vx,vy,vz,rel) 2048x2048x512 volume, z-slab sharded',
+}
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def load_reference():
+    """The UNMODIFIED reference module (baseline/_ref/calc_flow.py, copied verbatim from the reference checkout by
+    __graft_entry__.build(); git-ignored, travels to the GPU box).  Its two I/O-only imports that are not installed here
+    (tifffile, natsort) are stubbed; calc_flow2D / calc_flow3D do not use them.  None when the copy is absent."""
+    path = os.path.join(REF_DIR, 'calc_flow.py')
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    import types
+    for name, attrs in (('tifffile', {}), ('natsort', {'natsorted': sorted})):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                m = types.ModuleType(name)
+                m.__dict__.update(attrs)
+                sys.modules[name] = m
+    spec = importlib.util.spec_from_file_location('of3d_reference_calc_flow', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def peaks():
@@ -181,14 +212,28 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+_REF = None
+
+
+def cpu_kind():
+    return 'reference' if os.path.exists(os.path.join(REF_DIR, 'calc_flow.py')) else 'port'
+
+
 def _cpu_worker(args):
+    """One calc_flow call of the reference itself (baseline/_ref) or, when that copy is absent, of the oracle port"""
+    global _REF
     img, sig, ndim = args
-    from oracle import lk_oracle as orc
+    if _REF is None:
+        _REF = load_reference() or False
     t0 = time.perf_counter()
-    if ndim == 3:
-        orc.lk_flow3d(img, *sig, rel_mode='reference', use_scipy=True)
+    if _REF:
+        (_REF.calc_flow3D if ndim == 3 else _REF.calc_flow2D)(img, *sig)
     else:
-        orc.lk_flow2d(img, *sig, use_scipy=True)
+        from oracle import lk_oracle as orc
+        if ndim == 3:
+            orc.lk_flow3d(img, *sig, rel_mode='reference', use_scipy=True)
+        else:
+            orc.lk_flow2d(img, *sig, use_scipy=True)
     return time.perf_counter() - t0
 
 
@@ -233,17 +278,20 @@ def reference_arm(args, rank):
         return
     for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
         os.environ.setdefault(k, '1')       # the reference is single-threaded; we scale by processes instead
-    cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1)))
+    # a fixed core count (default 16, or all if the box has fewer) keeps the arm comparable between boxes
+    cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or 16))
     w = WORKLOADS[args.workload]
     # ~0.12 Mvox/s/core for the 3D path (BASELINE.md probe): ~0.5 Mvox per core per step is ~4-5 s
     v, ms, sample = run_cpu(args.workload, cores, args.steps, min(args.warmup, 1), args.cpu_voxels)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'impl': 'reference', 'metric': METRICS[args.workload], 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': args.workload, 'shape': list(w['shape']), 'sigmas': list(w['sig']), 'input_dtype': 'uint16',
-                   'note': 'CPU arm: each step = one cropped window per core (bounded sample); warmup capped at 1'},
-        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+                   'note': 'CPU arm: each step = one cropped window per core (bounded sample); warmup capped at 1; the '
+                           'reference is single-threaded, the cores run independent windows (its own parfor suggestion, '
+                           'calc_flow.py:512)', 'per_core_value': v / cores},
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': cpu_kind(), 'sample': sample},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -542,7 +590,7 @@ def gpu_arm(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_cpu_baseline:
         v, _, sample = run_cpu(args.workload, 1, 1, 0, args.cpu_voxels * 4)
-        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample}
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': cpu_kind(), 'sample': sample}
     print(json.dumps(line), flush=True)
 
 

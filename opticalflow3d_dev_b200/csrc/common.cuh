@@ -153,11 +153,11 @@ static inline bool fast_supported(const of3d_taps* t) {
 }
 // workspace volumes of compute type used by run_fast on a whole volume (excluding ic and dt0)
 static inline int fast_volumes(int ndim) { return ndim == 3 ? 9 + 4 : 3; }
-// The z march can read the raw frames itself (kernels_tz.cuh) when they are 8/16-bit integers, every frame and row is
+// The z march can read the raw frames itself (kernels_tz.cuh) when they are 8/16-bit unsigned integers, every frame and row is
 // 16-byte aligned, the window has at most kFusedMaxFrames frames and T is antisymmetric bit for bit with a zero centre
 constexpr int kFusedMaxFrames = 24;
 static inline bool fused_temporal_ok(const of3d_taps* t, const FramePtrs& fp, int in_dtype, int64_t nx) {
-    const int sz = in_dtype == OF3D_U8 ? 1 : ((in_dtype == OF3D_U16 || in_dtype == OF3D_I16) ? 2 : 0);
+    const int sz = in_dtype == OF3D_U8 ? 1 : (in_dtype == OF3D_U16 ? 2 : 0);
     if (!sz || t->nT > kFusedMaxFrames || (nx * sz) % 16 != 0 || !taps_symmetric(t->T, t->nT, -1.0) || t->T[t->nT / 2] != 0.0) return false;
     for (int k = 0; k < t->nT; ++k)
         if (reinterpret_cast<uintptr_t>(fp.p[k]) % 16) return false;

@@ -83,7 +83,14 @@ class _FrameSource:
 
 
 def process_flow(imDir, imName, fileType="SequenceT", spatialDimensions=3, xyzSig=3, tSig=1, wSig=4, *,
-                 precision='fp64', device=None, writers=4, verbose=True):
+                 precision='fp64', device=None, writers=4, verbose=True, frame_step=1):
+    """Reference calc_flow.py:362-625.  Keyword-only extras: precision / device as in calc_flow3D; writers = TIFF writer
+    threads; frame_step = d analyses every centre frame c on the frames c + d*(-R..R) (strided time sampling, the
+    frame-interval study of src/PublicationFigureScripts/plot_FigureS2_dt.m:54 `tNow = Ntslice+dtNow*(-3:3)`): the
+    first and last d*NtSlice frames are skipped and the output files keep the centre's frame index."""
+    frame_step = int(frame_step)
+    if frame_step < 1:
+        raise ValueError('frame_step must be a positive integer')
     ### Check inputs and set up paths (calc_flow.py:413-442) ########################################
     imDir = Path(imDir)
     if not imDir.is_dir():
@@ -96,7 +103,7 @@ def process_flow(imDir, imName, fileType="SequenceT", spatialDimensions=3, xyzSi
         if len(fileList) > 1:
             sys.exit('ERROR: Type is OneTif but more than one file was found for imName: ' + imName)
     elif fileType == 'SequenceT':
-        if len(fileList) < 6 * tSig + 1:
+        if len(fileList) < 6 * tSig + 1:               # (the reference's check; frame_step > 1 may need more, see n_out)
             sys.exit('ERROR: Image sequence found for file name ' + imName + ' only contains ' + str(len(fileList))
                      + ' files. Minimum 6*tsig+1 (' + str(6 * tSig + 1) + ') files required.')
     else:
@@ -146,17 +153,17 @@ def process_flow(imDir, imName, fileType="SequenceT", spatialDimensions=3, xyzSi
     say('Note: regardless of input filenames, the first image = frame 0.')
     say('If your file names start from 0, adjust indexing accordingly for reading the output files.')
     say(' ')
-    for hh in range(0, NtSlice):
+    for hh in range(0, min(NtSlice * frame_step, Nt)):
         say(str(datetime.now()) + ' - No data will be saved for frame ' + str(hh) + ' to avoid edge effects')
 
     ### Streaming processing loop ####################################################################
-    n_out = Nt - NtChunk + 1
+    n_out = Nt - (NtChunk - 1) * frame_step                    # centres NtSlice*d .. Nt-1-NtSlice*d
     if n_out > 0:
         lo, hi = shard_range(n_out, rank, world)               # this rank's window starts hh in [lo, hi)
         if hi > lo:
             _stream(imDir, fileList, fileType, spatialDimensions, (Nt, Nz, Ny, Nx), (xyzSig, tSig, wSig), NtChunk, NtSlice,
-                    range(lo, hi), savedir, imNameSave, precision, device, writers, verbose)
-    for hh in range(max(Nt - NtSlice, 0), Nt):
+                    range(lo, hi), savedir, imNameSave, precision, device, writers, verbose, frame_step)
+    for hh in range(max(Nt - NtSlice * frame_step, 0), Nt):
         say(str(datetime.now()) + ' - No data will be saved for frame ' + str(hh) + ' to avoid edge effects')
 
 
@@ -174,11 +181,15 @@ class FlowStream:
     * when a window is complete, of3d_flow_frames is enqueued on the library's stream (asynchronous mode) into one of
       two device output sets, and the device->host copy of that set runs on a second copy stream while the NEXT
       window computes;
-    * results are returned one call later as views of pinned host buffers; three host buffer sets rotate, so a
-      returned result stays valid during the NEXT call of push() -- copy it or finish writing it before the one after.
+    * results are returned one call later.  By default (copy=False) they are VIEWS of pinned host buffers: three host
+      buffer sets rotate, so a returned result stays valid during the NEXT call of push() and is overwritten by the
+      one after -- finish with it (or copy it) before that.  copy=True returns ordinary arrays that the caller owns.
+    * frame_step = d: the window of centre c is c + d*(-R..R) (plot_FigureS2_dt.m:54); the ring then holds (Kt-1)*d+1 frames.
+    The engine owns a private library context (its asynchronous mode never leaks into calc_flow3D calls of the same
+    thread); use it as a context manager or call close().
     """
 
-    def __init__(self, spatial_shape, dtype, sigmas, precision='fp64', device=None):
+    def __init__(self, spatial_shape, dtype, sigmas, precision='fp64', device=None, frame_step=1, copy=False):
         import torch
         self.torch = torch
         self.sp = tuple(int(v) for v in spatial_shape)
@@ -190,9 +201,14 @@ class FlowStream:
             raise TypeError('unsupported frame dtype %s' % self.in_dt)
         self.code = _lib.DTYPE_CODES[self.in_dt]
         self.dev = (int(os.environ.get('OF3D_DEVICE', os.environ.get('LOCAL_RANK', 0))) if device is None else int(device))
-        self.ctx = _lib.get_context(self.dev)
+        self.ctx = _lib.Context(self.dev)                  # private: async mode and workspace are this engine's own
         self.taps, self._keep = _lib.make_taps(flow_taps(*sigmas))
         self.kt = self._keep[3].size
+        self.step = int(frame_step)
+        if self.step < 1:
+            raise ValueError('frame_step must be a positive integer')
+        self.span = (self.kt - 1) * self.step + 1          # frames between the first and the last frame of a window
+        self.copy = bool(copy)
         self.precision = precision
         self.prec = _lib.FP64 if precision == 'fp64' else _lib.FP32
         self.odt = np.dtype(np.float64 if precision == 'fp64' else np.float32)
@@ -201,7 +217,7 @@ class FlowStream:
         tdev = torch.device('cuda', self.dev)
         self.tdev = tdev
         fbytes = self.nvox * self.in_dt.itemsize
-        self.ring = torch.empty((self.kt, fbytes), dtype=torch.uint8, device=tdev)       # frame t lives in slot t % kt
+        self.ring = torch.empty((self.span, fbytes), dtype=torch.uint8, device=tdev)     # frame t lives in slot t % span
         self.stage = [_lib.pinned_empty(self.sp, self.in_dt) for _ in range(2)]
         self.stage_ev = [None, None]
         # 3D reliability leaves the device as float32, the dtype the reference returns (calc_flow.py:355-357)
@@ -227,7 +243,10 @@ class FlowStream:
         centre, hslot, ev = self.pending
         ev.synchronize()
         self.pending = None
-        return centre, tuple(self.h_out[hslot])
+        return centre, self._result(hslot)
+
+    def _result(self, hslot):
+        return tuple(np.array(a) for a in self.h_out[hslot]) if self.copy else tuple(self.h_out[hslot])
 
     def staging(self):
         """The page-locked staging array the NEXT push may be given (filled by the caller, e.g. read from a file
@@ -256,23 +275,23 @@ class FlowStream:
         with torch.cuda.stream(self.s_in):
             if self.ring_free_ev is not None:
                 self.s_in.wait_event(self.ring_free_ev)    # the window that read this ring slot has been computed
-            self.ring[self.t % self.kt].copy_(torch.from_numpy(src.reshape(-1).view(np.uint8)), non_blocking=True)
+            self.ring[self.t % self.span].copy_(torch.from_numpy(src.reshape(-1).view(np.uint8)), non_blocking=True)
             ev = torch.cuda.Event(); ev.record(self.s_in)
         self.stage_ev[k] = ev
         self.h2d_bytes += src.nbytes
         self.t += 1
-        if self.t < self.kt:
+        if self.t < self.span:
             return None
-        # ---- a window is complete: frames t-kt .. t-1, centre t-1-kt//2.  Its compute and its D2H are enqueued BEFORE
+        # ---- a window is complete: frames t-span, t-span+d, .. t-1, centre t-1-(kt//2)*d.  Its compute and its D2H are enqueued BEFORE
         # the previous result is waited for, so the output copy stream never idles: D2H(t-1) overlaps compute(t).
         prev, self.pending = self.pending, None
         slot = self.nwin % 2                               # device output set
         hslot = self.nwin % 3                              # host output set
-        first = self.t - self.kt
+        first = self.t - self.span
         self.s_lib.wait_event(ev)                          # all uploads so far (same stream order) have landed
         if self.slot_free_ev[slot] is not None:
             self.s_lib.wait_event(self.slot_free_ev[slot])
-        ptrs = (C.c_void_p * self.kt)(*[self.ring[(first + i) % self.kt].data_ptr() for i in range(self.kt)])
+        ptrs = (C.c_void_p * self.kt)(*[self.ring[(first + i * self.step) % self.span].data_ptr() for i in range(self.kt)])
         o = [C.c_void_p(x.data_ptr()) for x in self.d_out[slot]]
         if self.ndim == 2:
             o = [o[0], o[1], None, o[2]]
@@ -289,23 +308,34 @@ class FlowStream:
                 self.d2h_bytes += h.nbytes
             dev_ = torch.cuda.Event(); dev_.record(self.s_out)
         self.slot_free_ev[slot] = dev_
-        self.pending = (first + self.kt // 2, hslot, dev_)
+        self.pending = (first + (self.kt // 2) * self.step, hslot, dev_)
         self.nwin += 1
         if prev is None:
             return None
         prev[2].synchronize()                              # D2H of the previous window has landed
-        return prev[0], tuple(self.h_out[prev[1]])
+        return prev[0], self._result(prev[1])
 
     def flush(self):
         return self._collect()
 
     def close(self):
-        self.ctx.sync()
-        self.ctx.set_async(False)
+        if self.ctx is not None:
+            try:
+                self.ctx.sync()
+            finally:
+                self.ctx.close()
+                self.ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
 
 def _stream(imDir, fileList, fileType, ndim, dims, sig, NtChunk, NtSlice, starts, savedir, name, precision, device, writers,
-            verbose):
+            verbose, frame_step=1):
     Nt, Nz, Ny, Nx = dims
     src = _FrameSource(imDir, fileList, fileType, Nt, Nz, ndim)
     sp = (Nz, Ny, Nx) if ndim == 3 else (Ny, Nx)
@@ -313,9 +343,16 @@ def _stream(imDir, fileList, fileType, ndim, dims, sig, NtChunk, NtSlice, starts
     if first.shape != sp:
         sys.exit('ERROR: frame shape %s does not match the metadata %s' % (first.shape, sp))
     in_dt = first.dtype if first.dtype in _lib.DTYPE_CODES else np.dtype(np.float64)
-    eng = FlowStream(sp, in_dt, sig, precision=precision, device=device)
-    kt = eng.kt
-    off = NtSlice - kt // 2                                    # first frame of a window the t-filter touches
+    eng = FlowStream(sp, in_dt, sig, precision=precision, device=device, frame_step=frame_step)
+    try:
+        _stream_loop(eng, src, ndim, in_dt, NtSlice, starts, savedir, name, writers, verbose, frame_step)
+    finally:
+        eng.close()                                            # also on a writer / reader error: nothing stays asynchronous
+
+
+def _stream_loop(eng, src, ndim, in_dt, NtSlice, starts, savedir, name, writers, verbose, d):
+    kt, span = eng.kt, eng.span
+    off = (NtSlice - kt // 2) * d                              # first frame of window 0 the t-filter touches
     names = ['vx', 'vy', 'vz', 'rel'] if ndim == 3 else ['vx', 'vy', 'rel']
     t_start = {}
 
@@ -336,16 +373,16 @@ def _stream(imDir, fileList, fileType, ndim, dims, sig, NtChunk, NtSlice, starts
                 print(str(datetime.now()) + ' - Frame ' + str(centre) + ' saved.  Duration: ' + str(datetime.now() - t_start[centre]))
         return wait
 
-    # frames needed by this rank: window starts hh in `starts` touch frames hh+off .. hh+off+kt-1
-    t_lo, t_hi = starts[0] + off, starts[-1] + off + kt
+    # frames needed by this rank: window start hh touches frames hh+off, hh+off+d, .. hh+off+span-1
+    t_lo, t_hi = starts[0] + off, starts[-1] + off + span
     from collections import deque
     with ThreadPoolExecutor(max_workers=max(1, int(writers))) as pool:
         futs = deque()                                     # timepoints being written; a result stays valid for one more push
         for t in range(t_lo, t_hi):
             while len(futs) > 1:
                 futs.popleft()()
-            centre_next = t - (kt - 1) + kt // 2           # centre of the window this frame completes
-            if t - t_lo >= kt - 1:
+            centre_next = t - (span - 1) + (kt // 2) * d   # centre of the window this frame completes
+            if t - t_lo >= span - 1:
                 t_start[centre_next] = datetime.now()
                 if verbose:
                     print(str(datetime.now()) + ' - Processing frame ' + str(centre_next) + '...')
@@ -361,4 +398,3 @@ def _stream(imDir, fileList, fileType, ndim, dims, sig, NtChunk, NtSlice, starts
             futs.append(write_all(pool, done[1], done[0]))
         for f in futs:
             f()
-    eng.close()

@@ -1,6 +1,7 @@
-"""CPU tests (gloo, world_size 2 and 3) of the N>1 host logic: timepoint sharding, z-slab planning, halo
-exchange and cropping.  The compute stages are injected (the oracle, on CPU tensors) -- the product path uses
-the CUDA library; what is under test here is that slab + halo + crop reproduces the unsharded result exactly."""
+"""CPU tests (gloo, world_size 2 and 3) of the N>1 host logic: timepoint sharding, z-slab planning, the in-place halo
+exchange of the raw frames and the owned-range crop.  The compute stage is injected (the oracle, on CPU tensors) -- the
+product path uses the CUDA library; what is under test here is that slab + halo + crop reproduces the unsharded
+result exactly, including a stack with more frames than the temporal filter touches and a strided input."""
 import os
 import socket
 
@@ -41,33 +42,10 @@ def _free_port():
     s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _oracle_temporal(fr, sig):
-    img = fr.numpy().astype(np.float64)
-    tp = orc.make_taps(*sig)
-    c = img.shape[0] // 2
-    rt = tp['T'].size // 2
-    dt0 = orc.correlate1d_nearest(img[c - rt:c + rt + 1], tp['T'], 0)[rt]
-    return torch.from_numpy(np.ascontiguousarray(img[c])), torch.from_numpy(np.ascontiguousarray(dt0))
-
-
-def _oracle_spatial(ic, dt0, sig):
-    """Spatial stages of the oracle on (ic, dt0): same code path as lk_flow3d after the temporal stage."""
-    tp = orc.make_taps(*sig)
-    D, S, G, W = tp['D'], tp['S'], tp['G'], tp['W']
-    corr = orc.correlate1d_nearest
-    ic, dt0 = ic.numpy(), dt0.numpy()
-    ch = lambda a, f: orc._chain(a, [(f[0], 1), (f[1], 2), (f[2], 0)], corr)
-    dt, dy, dx, dz = ch(dt0, (G, G, G)), ch(ic, (D, S, S)), ch(ic, (S, D, S)), ch(ic, (S, S, D))
-    win = lambda p: ch(p, (W, W, W))
-    tx, ty, tz = win(dx * dt), win(dy * dt), win(dz * dt)
-    xy, xz, xx, yz, yy, zz = win(dx * dy), win(dx * dz), win(dx * dx), win(dy * dz), win(dy * dy), win(dz * dz)
-    det = (xx * yy * zz) + (2 * xy * xz * yz) - (yy * xz ** 2) - (zz * xy ** 2) - (xx * yz ** 2)
-    inv = (det + orc.EPS) ** -1
-    vx = -inv * ((yy * zz - yz * yz) * tx + (xz * yz - xy * zz) * ty + (xy * yz - xz * yy) * tz)
-    vy = -inv * ((yz * xz - xy * zz) * tx + (xx * zz - xz * xz) * ty + (xz * xy - xx * yz) * tz)
-    vz = -inv * ((xy * yz - yy * xz) * tx + (xy * xz - xx * yz) * ty + (xx * yy - xy * xy) * tz)
-    rel = orc.min_eig_sym3(xx, xy, xz, yy, yz, zz, 'float64')
-    return [torch.from_numpy(np.ascontiguousarray(a)) for a in (vx, vy, vz, rel)]
+def _oracle_flow(ext, own_lo, own_n, sig):
+    """The oracle on the extended window, cropped to the owned planes: what of3d_flow3d_slab does on the device."""
+    out = orc.lk_flow3d(ext.numpy(), *sig, rel_mode='float64')
+    return [torch.from_numpy(np.ascontiguousarray(o[own_lo:own_lo + own_n])) for o in out]
 
 
 def _worker(rank, world, port, shape, sig, seed, q):
@@ -76,10 +54,9 @@ def _worker(rank, world, port, shape, sig, seed, q):
     try:
         img = make_stack(shape, seed=seed, dtype=np.uint16)
         z0, z1 = multigpu.shard_timepoints(shape[1], world)[rank]
-        local = torch.from_numpy(img[:, z0:z1].astype(np.int32))
+        local = torch.from_numpy(img.astype(np.int32))[:, z0:z1]      # a strided (non-contiguous) view of the stack
         out = multigpu.calc_flow3D_zslab(local, *sig, nz_total=shape[1],
-                                         temporal_fn=lambda fr: _oracle_temporal(fr, sig),
-                                         spatial_fn=lambda a, b: _oracle_spatial(a, b, sig))
+                                         flow_fn=lambda ext, lo, n: _oracle_flow(ext, lo, n, sig))
         q.put((rank, [o.numpy() for o in out]))
         dist.barrier()
     finally:
@@ -88,7 +65,7 @@ def _worker(rank, world, port, shape, sig, seed, q):
 
 @pytest.mark.parametrize('world', [2, 3])
 def test_zslab_halo_exchange_matches_unsharded(world):
-    shape, sig, seed = (7, 24, 20, 22), (1, 1, 1.3), 5         # halo = 3 + 4 = 7 planes, 8 planes per rank at world 3
+    shape, sig, seed = (9, 24, 20, 22), (1, 1, 1.3), 5         # halo = 3 + 4 = 7 planes, 8 planes per rank at world 3; 9 frames, 7 used
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
