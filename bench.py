@@ -122,26 +122,29 @@ def alg_fma_per_voxel(sig, ndim):
     kt = 2 * math.ceil(3 * sig[1]) + 1
     kw = 2 * math.ceil(3 * sig[2]) + 1
     if ndim == 3:
-        return (kt - 1) + 3 * kr + 3 * kr + 6 * ks + 9 + 27 * kw + 120
+        return (kt - 1) + 3 * kr + 3 * kr + 6 * ks + 9 + 27 * kw + 120    # (the z-first order needs 13 fewer)
     return (kt - 1) + 2 * kr + 2 * kr + 2 * ks + 5 + 10 * kw + 30
 
 
-def stage_model(sig, ndim, precision, in_itemsize=2):
+def stage_model(sig, ndim, precision, in_itemsize=2, fused=True):
     """Per-stage algorithmic bytes and FMAs per voxel of the marching pipeline: every stage reads its
-    inputs once and writes its outputs once; FMA counts are those of the direct separable evaluation the stage performs."""
+    inputs once and writes its outputs once; FMA counts are those of the direct separable evaluation the stage performs.
+    3D runs z first: temporal derivative + three z filters in one kernel, then four in-plane kernels."""
     e = 8 if precision == 'fp64' else 4
     kr = 2 * math.ceil(3 * sig[0]) + 1
     ks = 2 * math.ceil(3 * sig[0] / 4) + 1
     kt = 2 * math.ceil(3 * sig[1]) + 1
     kw = 2 * math.ceil(3 * sig[2]) + 1
     if ndim == 3:
-        return {'temporal': (kt * in_itemsize + 2 * e, kt - 1),
-                'gradient_xy': (2 * e + 4 * e, 4 * kr + 3 * ks),
-                'gradient_z': (4 * e + 4 * e, 2 * kr + 2 * ks),
-                'products_window_z': (4 * e + 9 * e, 9 + 9 * kw),
-                'window_xy_solve': (9 * e + 4 * e, 18 * kw + 120)}
+        m = {'gradient_z': ((kt * in_itemsize if fused else 2 * e) + 3 * e, (kt - 1 if fused else 0) + 2 * kr + ks),
+             'gradient_xy': (4 * e + 4 * e, 4 * kr + 4 * ks),
+             'products_window_z': (4 * e + 9 * e, 9 + 9 * kw),
+             'window_xy_solve': (9 * e + 4 * e, 18 * kw + 120)}
+        if not fused:
+            m['temporal'] = (kt * in_itemsize + 2 * e, kt - 1)
+        return m
     return {'temporal': (kt * in_itemsize + 2 * e, kt - 1),
-            'gradient_xy': (2 * e + 3 * e, 4 * kr + 2 * ks),
+            'gradient_xy': (3 * e + 3 * e, 4 * kr + 2 * ks),
             'window_xy_solve': (3 * e + 3 * e, 5 + 10 * kw + 30)}
 
 
@@ -299,9 +302,138 @@ def reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, steps, warmup, chunk_planes, seed=1005):
+    """ONE output timepoint of a (kt, nz_total, ny, nx) uint16 window sharded by z-slab over the ranks of the default
+    process group: every step = in-library NCCL halo exchange of the raw frames (straight into each rank's extended
+    buffer, asynchronous) + of3d_flow3d_slab on the owned planes (chunks that do not touch a halo run during the
+    exchange).  Returns the record on rank 0 (None elsewhere).  Also checks, untimed: (a) the received halo planes equal
+    the planes the neighbour generated, (b) on a small volume, the sharded result is bit-identical to the single-GPU one."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from opticalflow3d_dev_b200 import _lib, multigpu
+    from opticalflow3d_dev_b200.calc_flow import calc_flow3D
+    dev = torch.device('cuda', local_rank)
+    ctx = _lib.get_context(local_rank)
+
+    def fill(zs_, z0, nzt):
+        """this rank's owned planes of every frame, generated on the device"""
+        own = zs_.own_frames()
+        tmp = torch.empty((zs_.own, zs_.ny, zs_.nx), dtype=torch.uint16, device=dev)
+        for k in range(zs_.kt):
+            torch.cuda.synchronize()
+            _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, tmp.data_ptr(), 1, zs_.own, zs_.ny, zs_.nx, k, z0, seed), 'synth')
+            own[k].copy_(tmp)
+        torch.cuda.synchronize()
+        return tmp
+
+    # ---- (b) parity on a small volume: sharded == unsharded, bit for bit
+    H = multigpu.halo_planes(sig[0], sig[2])
+    pn = (H + 7) * world
+    small = multigpu.ZSlab(pn, 96, 128, np.uint16, sig, precision=precision, device=local_rank, chunk_planes=16, rel_dtype='float64')
+    fill(small, small.z0, pn)
+    small.exchange()
+    part = small.flow()
+    ctx.sync()
+    parity = None
+    gathered = [[torch.empty((multigpu.shard_timepoints(pn, world)[r][1] - multigpu.shard_timepoints(pn, world)[r][0], 96, 128),
+                             dtype=part[0].dtype, device=dev) for r in range(world)] if rank == 0 else None for _ in range(4)]
+    for i in range(4):
+        dist.gather(part[i].contiguous(), gathered[i], dst=0)
+    if rank == 0:
+        full = torch.empty((small.kt, pn, 96, 128), dtype=torch.uint16, device=dev)
+        torch.cuda.synchronize()
+        _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, full.data_ptr(), small.kt, pn, 96, 128, 0, 0, seed), 'synth')
+        ref = calc_flow3D(full, *sig, precision=precision, rel_dtype='float64', device=local_rank)
+        parity = all(torch.equal(torch.cat(gathered[i], 0), ref[i]) for i in range(4))
+        del full, ref
+    small.close()
+    del small, part, gathered
+    torch.cuda.empty_cache()
+
+    # ---- the measured volume
+    zs_ = multigpu.ZSlab(nz_total, ny, nx, np.uint16, sig, precision=precision, device=local_rank, chunk_planes=chunk_planes,
+                         rel_dtype='float64')
+    tmp = fill(zs_, zs_.z0, nz_total)
+    outs = None
+
+    def step():
+        zs_.exchange()
+        return zs_.flow(out=outs)
+
+    def barrier():
+        ctx.sync(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+
+    outs = list(step())
+    ctx.sync()
+    # ---- (a) the halo planes that arrived are the neighbour's planes
+    halo_ok = True
+    if zs_.lo:
+        chk = torch.empty((zs_.lo, ny, nx), dtype=torch.uint16, device=dev)
+        torch.cuda.synchronize()
+        _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, chk.data_ptr(), 1, zs_.lo, ny, nx, zs_.kt - 1, zs_.z0 - zs_.lo, seed), 'synth')
+        halo_ok = halo_ok and bool(torch.equal(chk, zs_.frames[zs_.kt - 1, :zs_.lo]))
+        del chk
+    if zs_.hi:
+        chk = torch.empty((zs_.hi, ny, nx), dtype=torch.uint16, device=dev)
+        torch.cuda.synchronize()
+        _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, chk.data_ptr(), 1, zs_.hi, ny, nx, 0, zs_.z1, seed), 'synth')
+        halo_ok = halo_ok and bool(torch.equal(chk, zs_.frames[0, zs_.lo + zs_.own:]))
+        del chk
+    del tmp
+    for _ in range(max(warmup - 1, 0)):
+        step()
+    barrier()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    ctx.set_async(True)
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    ctx.set_async(False)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    stat = torch.tensor([ms, float(ctx.launch_count() - l0), 0.0 if halo_ok else 1.0], dtype=torch.float64, device=dev)
+    tmax = stat.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(stat, op=dist.ReduceOp.SUM)
+    mem = torch.cuda.mem_get_info(local_rank)
+    zs_.close()
+    del zs_, outs
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    vol = nz_total * ny * nx
+    value = vol * steps / (float(tmax[0].item()) * 1e-3)
+    peak, peak_src = peaks()
+    bpv = alg_bytes_per_voxel(sig, 3, precision)
+    fma = alg_fma_per_voxel(sig, 3)
+    fpk = fma_peak(precision)
+    es = 2
+    kt = 2 * math.ceil(3 * sig[1]) + 1
+    return {
+        'metric': 'output voxels/s (vx,vy,vz,rel) %dx%dx%d volume, z-slab sharded' % (nx, ny, nz_total), 'value': value, 'unit': UNIT,
+        'n_gpus': world, 'steps': steps, 'ms_per_step': float(tmax[0].item()) / steps, 'scaling': 'weak' if nz_total != 512 else 'strong',
+        'dtype': 'f64' if precision == 'fp64' else 'f32',
+        'config': {'shape': [kt, nz_total, ny, nx], 'sigmas': list(sig), 'input_dtype': 'uint16', 'planes_per_rank': nz_total // world,
+                   'chunk_planes': chunk_planes,
+                   'sharding': 'z-slab; %d raw halo planes of each of the %d frames exchanged with each neighbour by the '
+                               'library (grouped ncclSend/ncclRecv, in place); interior chunks overlap the exchange' % (H, kt),
+                   'halo_bytes_per_rank_per_step': int(2 * H * kt * ny * nx * es)},
+        'parity_small_volume_bit_identical': parity, 'halo_planes_verified': bool(stat[2].item() == 0.0),
+        'free_hbm_bytes_rank0_after': int(mem[0]),
+        'roofline': {'bound': 'hbm', 'achieved': value * bpv / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
+                     'frac': value * bpv / 1e9 / world / peak, 'peak_source': peak_src, 'alg_bytes_per_voxel': bpv,
+                     'fp_pipe': {'alg_fma_per_voxel': fma, 'achieved_tfma_per_s': value * fma / 1e12 / world,
+                                 'peak_tfma_per_s': fpk, 'frac': value * fma / 1e12 / world / fpk}},
+        'gpu_launches': int(stat[1].item()),
+    }
+
+
 def zslab_arm(args, rank, world, local_rank):
-    """cfg5: ONE output timepoint of a volume sharded by z-slab; every step = temporal stage on the owned planes,
-    NCCL halo exchange of (ic, dt0) with the two neighbours, spatial stages on the extended slab, crop."""
+    """--workload cfg5: the 2048x2048x512 window of BASELINE config 5 over 2/4/8 GPUs"""
     import torch
     import torch.distributed as dist
     from opticalflow3d_dev_b200.build import build_library
@@ -311,74 +443,156 @@ def zslab_arm(args, rank, world, local_rank):
         raise SystemExit('workload cfg5 is z-slab sharded and needs --gpus >= 2')
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     dist.barrier()
-    from opticalflow3d_dev_b200 import _lib, multigpu
     torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
     w = WORKLOADS[args.workload]
     nt, nz, ny, nx = w['shape']
-    sig = w['sig']
-    z0, z1 = multigpu.shard_timepoints(nz, world)[rank]
-    ctx = _lib.get_context(local_rank)
-    frames = torch.empty((nt, z1 - z0, ny, nx), dtype=torch.uint16, device=dev)
-    torch.cuda.synchronize()
-    _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, frames.data_ptr(), nt, z1 - z0, ny, nx, 0, z0, 1000 + 5), 'synth')
-
-    def step():
-        out = multigpu.calc_flow3D_zslab(frames, *sig, nz_total=nz, precision=args.precision)
-        return out
-
-    def barrier():
-        ctx.sync(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        o = step(); del o
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        o = step(); del o
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    rec = zslab_measure(rank, world, local_rank, w['sig'], nz, ny, nx, args.precision, args.steps, args.warmup, args.chunk_planes)
     clocks = sampler.stop() if rank == 0 else None
-    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-    lsum = torch.tensor([float(ctx.launch_count() - l0)], dtype=torch.float64, device=dev)
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
     if rank == 0:
-        vol = nz * ny * nx
-        value = vol * args.steps / (float(tmax.item()) * 1e-3)
-        peak, peak_src = peaks()
-        bpv = alg_bytes_per_voxel(sig, 3, args.precision)
-        fma = alg_fma_per_voxel(sig, 3)
-        fpk = fma_peak(args.precision)
-        halo = multigpu.halo_planes(sig[0], sig[2])
-        es = 8 if args.precision == 'fp64' else 4
-        line = {
-            'metric': 'output voxels/s (vx,vy,vz,rel) 2048x2048x512 volume, z-slab sharded', 'value': value, 'unit': UNIT,
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(tmax.item()) / args.steps,
-            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': 'f64' if args.precision == 'fp64' else 'f32', 'data': 'synthetic',
-            'config': {'workload': args.workload, 'shape': list(w['shape']), 'sigmas': list(sig), 'input_dtype': 'uint16',
-                       'sharding': 'z-slab, %d halo planes of (ic, dt0) exchanged with each neighbour over NCCL' % halo,
-                       'halo_bytes_per_rank_per_step': int(2 * 2 * halo * ny * nx * es)},
-            'roofline': {'bound': 'hbm', 'achieved': value * bpv / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
-                         'frac': value * bpv / 1e9 / world / peak, 'traffic': None, 'peak_source': peak_src,
-                         'alg_bytes_per_voxel': bpv,
-                         'fp_pipe': {'alg_fma_per_voxel': fma, 'achieved_tfma_per_s': value * fma / 1e12 / world,
-                                     'peak_tfma_per_s': fpk, 'frac': value * fma / 1e12 / world / fpk}},
-            'clocks': clocks, 'gpu_launches': int(lsum.item()), 'e2e': None,
-        }
+        line = dict(rec)
+        line.update({'warmup': args.warmup, 'higher_is_better': True, 'vs_baseline': None, 'data': 'synthetic', 'clocks': clocks, 'e2e': None})
+        line['config']['workload'] = args.workload
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
 
 
-def gpu_arm(args, rank, world, local_rank):
+def device_measure(ctx, local_rank, rank, world, workload, precision, timepoints, steps, warmup, generic=False, stage_events=True,
+                   sampler=None):
+    """Device-timed pass of one workload: every output timepoint of the (possibly shortened) time-lapse once per step,
+    sharded by output timepoint over the ranks, frames resident in HBM.  Returns a dict of raw measurements (this rank's)."""
     import ctypes as C
+    import torch
+    from opticalflow3d_dev_b200 import _lib
+    from opticalflow3d_dev_b200.taps import flow_taps
+    dev = torch.device('cuda', local_rank)
+    lib = ctx.lib
+    w = WORKLOADS[workload]
+    shape, sig = tuple(w['shape']), w['sig']
+    ndim = len(shape) - 1
+    rt = math.ceil(3 * sig[1])
+    kt = 2 * rt + 1
+    nt = shape[0] if timepoints is None else min(shape[0], timepoints + 2 * rt)
+    sp = shape[1:]
+    nz = sp[0] if ndim == 3 else 1
+    ny, nx = sp[-2], sp[-1]
+    vol = int(np.prod(sp))
+    outs_all = list(range(rt, nt - rt))                         # output timepoints of the time-lapse
+    per = [len(outs_all) // world + (1 if r < len(outs_all) % world else 0) for r in range(world)]
+    lo = sum(per[:rank]); mine = outs_all[lo:lo + per[rank]]
+    taps, keep = _lib.make_taps(flow_taps(*sig))
+    prec = _lib.FP64 if precision == 'fp64' else _lib.FP32
+    odt = torch.float64 if precision == 'fp64' else torch.float32
+    flags = _lib.FLAG_GENERIC if generic else 0
+
+    # this rank's frames [mine[0]-rt, mine[-1]+rt], generated on the device (uint16 stored in int16 tensors)
+    nloc = (len(mine) + 2 * rt) if mine else 0
+    frames = torch.empty((max(nloc, 1), nz, ny, nx), dtype=torch.int16, device=dev)
+    torch.cuda.synchronize()
+    if mine:
+        _lib.check(lib.of3d_synth_blobs(ctx.handle, frames.data_ptr(), nloc, nz, ny, nx, mine[0] - rt, 0, 1000 + int(workload[3:])), 'synth')
+    outs = [torch.empty((nz, ny, nx), dtype=odt, device=dev) for _ in range(ndim + 1)]
+    optr = [C.c_void_p(o.data_ptr()) for o in outs]
+    if ndim == 2:
+        optr = [optr[0], optr[1], None, optr[2]]
+    fbytes = vol * 2
+    torch.cuda.synchronize()
+    ctx.set_async(True)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    batch2d = 16 if (ndim == 2 and not generic and not os.environ.get('OF3D_BENCH_NO_BATCH2D')) else 0
+    if batch2d:                                                  # 2D time-lapse: 16 output timepoints per launch set
+        bouts = [torch.empty((batch2d, ny, nx), dtype=odt, device=dev) for _ in range(3)]
+
+    def one_pass():
+        if batch2d:
+            for j0 in range(0, len(mine), batch2d):
+                b = min(batch2d, len(mine) - j0)
+                ptrs = (C.c_void_p * (b + kt - 1))(*[frames.data_ptr() + (j0 + k) * fbytes for k in range(b + kt - 1)])
+                rc = lib.of3d_flow2d_batch(ctx.handle, ptrs, _lib.U16, b, ny, nx, C.byref(taps), prec, flags,
+                                           *[C.c_void_p(o.data_ptr()) for o in bouts])
+                _lib.check(rc, 'of3d_flow2d_batch')
+            return
+        for i in range(len(mine)):
+            ptrs = (C.c_void_p * kt)(*[frames.data_ptr() + (i + k) * fbytes for k in range(kt)])
+            rc = lib.of3d_flow_frames(ctx.handle, ndim, ptrs, _lib.U16, _lib.DEVICE, nz, ny, nx, C.byref(taps), prec, flags,
+                                      optr[0], optr[1], optr[2], optr[3], _lib.DEVICE)
+            _lib.check(rc, 'of3d_flow_frames')
+
+    def barrier():
+        ctx.sync(); torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(); torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        one_pass()
+    barrier()
+    if sampler is not None:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ctx.stage_times()                                            # clear the per-stage accumulators
+    ctx.set_profile(stage_events)                                # event brackets around every launch, on the library stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        one_pass()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    stages = ctx.stage_times()
+    ctx.set_profile(False)
+    ctx.set_async(False)
+    clocks = sampler.stop() if sampler is not None else None
+    return dict(ms=ms, launches=launches, stages=stages, clocks=clocks, n_out=len(outs_all), n_mine=len(mine), vol=vol, sig=sig,
+                ndim=ndim, nt=nt, sp=sp, kt=kt, rt=rt, frames=frames, nloc=nloc, batch2d=batch2d)
+
+
+def roofline_record(m, workload, precision, value, world, steps, full):
+    """`achieved` = the ALGORITHMIC bytes of the call (window read once, outputs written once:
+    alg_bytes_per_voxel x the voxels one launch processes) / the dominant kernel's launch time -- against the measured
+    copy peak.  What the kernel itself moves (its own inputs + outputs) is `kernel_local`; the roof that actually binds
+    (CUDA-core FMA issue) is `fp_pipe`; every stage is in `stages`, the whole pipeline in `pipeline`."""
+    peak, peak_src = peaks()
+    sig, ndim, vol = m['sig'], m['ndim'], m['vol']
+    bpv = alg_bytes_per_voxel(sig, ndim, precision)
+    ach = value * bpv / 1e9 / world                             # per-GPU algorithmic GB/s of the whole pipeline
+    fma = alg_fma_per_voxel(sig, ndim)
+    fpk = fma_peak(precision)
+    tr = measured_traffic(workload, precision) if full else None
+    pipeline = {'alg_bytes_per_voxel': bpv, 'alg_gbs': ach, 'hbm_frac': ach / peak,
+                'traffic_bytes_per_voxel': (tr['bytes_per_voxel'] if tr else None),
+                'alg_fma_per_voxel': fma, 'tfma_per_s': value * fma / 1e12 / world,
+                'fp_frac': (value * fma / 1e12 / world / fpk) if fpk else None,
+                'launch': 'one output timepoint = %s kernels' % (tr['kernels'] if tr else 'several')}
+    fused = 'temporal' not in m['stages']
+    rows = stage_report(m['stages'], stage_model(sig, ndim, precision, fused=fused), vol, m['n_mine'] * steps, peak, fpk)
+    top = next((r for r in rows if 'alg_gbs' in r), None)
+    if not top:                                                  # generic kernels / stage events disabled
+        return {'bound': 'hbm', 'kernel': 'whole pipeline', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                'traffic': (tr['bytes_per_voxel'] * vol if tr else None), 'peak_source': peak_src,
+                'alg_bytes_per_voxel': bpv, 'alg_bytes_per_launch': bpv * vol, 'stages': rows, 'pipeline': pipeline}
+    sd = (tr or {}).get('stage_dram_bytes_per_launch', {})
+    k_ach = bpv * vol / top['ms_per_timepoint'] / 1e6
+    return {'bound': 'hbm', 'kernel': top['stage'], 'achieved': k_ach, 'peak': peak, 'unit': 'GB/s', 'frac': k_ach / peak,
+            'traffic': sd.get(top['stage']), 'peak_source': peak_src,
+            'alg_bytes_per_voxel': bpv, 'alg_bytes_per_launch': bpv * vol,
+            'launch_ms': top['ms_per_timepoint'], 'share_of_step': top['ms_per_timepoint'] * m['n_mine'] * steps / m['ms'],
+            'note': 'achieved = algorithmic bytes of the call (SURVEY 8(d): %d B/voxel) x voxels per launch / the dominant '
+                    'kernel\'s launch time' % bpv,
+            'kernel_local': {'bytes_per_voxel': top['alg_bytes_per_voxel'], 'gbs': top['alg_gbs'], 'hbm_frac': top['hbm_frac'],
+                             'note': 'the kernel\'s own inputs + outputs (incl. the intermediates it exchanges with its neighbours)'},
+            'fp_pipe': {'alg_fma_per_voxel': top['alg_fma_per_voxel'], 'achieved_tfma_per_s': top['tfma_per_s'],
+                        'peak_tfma_per_s': fpk, 'frac': top['fp_frac'],
+                        'note': 'the roof that binds this kernel is the CUDA-core FMA pipe (measured peak, '
+                                'tools/fma_peak.cu), not HBM; see DESIGN.md 3.3'},
+            'stages': rows, 'pipeline': pipeline}
+
+
+def gpu_arm(args, rank, world, local_rank):
     import torch
     from opticalflow3d_dev_b200.build import build_library
     if rank == 0:
@@ -389,90 +603,31 @@ def gpu_arm(args, rank, world, local_rank):
         dist.barrier()
     from opticalflow3d_dev_b200 import _lib
     from opticalflow3d_dev_b200.calc_flow import calc_flow2D, calc_flow3D
-    from opticalflow3d_dev_b200.taps import flow_taps
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     from opticalflow3d_dev_b200 import numa
     cpus = numa.bind_to_device(local_rank) if world > 1 else None   # pinned buffers and copy threads on the GPU's NUMA node
-    w = WORKLOADS[args.workload]
-    shape, sig = tuple(w['shape']), w['sig']
-    ndim = len(shape) - 1
-    nt = shape[0] if args.timepoints is None else min(shape[0], args.timepoints + 2 * math.ceil(3 * sig[1]))
-    sp = shape[1:]
-    nz = sp[0] if ndim == 3 else 1
-    ny, nx = sp[-2], sp[-1]
-    vol = int(np.prod(sp))
-    rt = math.ceil(3 * sig[1])
-    kt = 2 * rt + 1
-    outs_all = list(range(rt, nt - rt))                         # output timepoints of the time-lapse
-    per = [len(outs_all) // world + (1 if r < len(outs_all) % world else 0) for r in range(world)]
-    lo = sum(per[:rank]); mine = outs_all[lo:lo + per[rank]]
-
     ctx = _lib.get_context(local_rank)
-    lib = ctx.lib
-    tp = flow_taps(*sig)
-    taps, keep = _lib.make_taps(tp)
-    prec = _lib.FP64 if args.precision == 'fp64' else _lib.FP32
-    odt = torch.float64 if args.precision == 'fp64' else torch.float32
-    flags = _lib.FLAG_GENERIC if args.generic else 0
-
-    # this rank's frames [mine[0]-rt, mine[-1]+rt], generated on the device (uint16 stored in int16 tensors)
-    nloc = (len(mine) + 2 * rt) if mine else 0
-    frames = torch.empty((max(nloc, 1), nz, ny, nx), dtype=torch.int16, device=dev)
-    torch.cuda.synchronize()
-    if mine:
-        _lib.check(lib.of3d_synth_blobs(ctx.handle, frames.data_ptr(), nloc, nz, ny, nx, mine[0] - rt, 0, 1000 + 4), 'synth')
-    outs = [torch.empty((nz, ny, nx), dtype=odt, device=dev) for _ in range(ndim + 1)]
-    optr = [C.c_void_p(o.data_ptr()) for o in outs]
-    if ndim == 2:
-        optr = [optr[0], optr[1], None, optr[2]]
-    fbytes = vol * 2
-    torch.cuda.synchronize()
-    ctx.set_async(True)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-
-    def one_pass():
-        for i in range(len(mine)):
-            ptrs = (C.c_void_p * kt)(*[frames.data_ptr() + (i + k) * fbytes for k in range(kt)])
-            rc = lib.of3d_flow_frames(ctx.handle, ndim, ptrs, _lib.U16, _lib.DEVICE, nz, ny, nx, C.byref(taps), prec, flags,
-                                      optr[0], optr[1], optr[2], optr[3], _lib.DEVICE)
-            _lib.check(rc, 'of3d_flow_frames')
+    m = device_measure(ctx, local_rank, rank, world, args.workload, args.precision, args.timepoints, args.steps, args.warmup,
+                       generic=args.generic, stage_events=not args.no_stage_events, sampler=ClockSampler(local_rank) if rank == 0 else None)
+    sig, ndim, vol, sp, kt, rt, nt = m['sig'], m['ndim'], m['vol'], m['sp'], m['kt'], m['rt'], m['nt']
+    frames, nloc, clocks = m['frames'], m['nloc'], m['clocks']
+    mine_n = m['n_mine']
+    tmax = torch.tensor([m['ms']], dtype=torch.float64, device=dev)
+    lsum = torch.tensor([float(m['launches'])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
+    ms_total = float(tmax.item())
+    ms = m['ms']
+    total_vox = m['n_out'] * vol * args.steps
+    value = total_vox / (ms_total * 1e-3)
 
     def barrier():
         ctx.sync(); torch.cuda.synchronize()
         if world > 1:
             dist.barrier(); torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        one_pass()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    l0 = ctx.launch_count()
-    ctx.stage_times()                                            # clear the per-stage accumulators
-    ctx.set_profile(not args.no_stage_events)                    # event brackets around every launch, on the library stream
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        one_pass()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count() - l0
-    stages = ctx.stage_times()
-    ctx.set_profile(False)
-    clocks = sampler.stop() if rank == 0 else None
-    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-    lsum = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
-    ms_total = float(tmax.item())
-    total_vox = len(outs_all) * vol * args.steps
-    value = total_vox / (ms_total * 1e-3)
-    ctx.set_async(False)
 
     # ---- end-to-end with HOST buffers, copies inside the timed region, two public entry points:
     #   stream : FlowStream (the engine under process_flow): every frame uploaded once from pinned memory, results
@@ -481,7 +636,7 @@ def gpu_arm(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         from opticalflow3d_dev_b200.timelapse import FlowStream
-        n_e2e = max(1, min(args.e2e_timepoints, len(mine))) if mine else 0
+        n_e2e = max(1, min(args.e2e_timepoints, mine_n)) if mine_n else 0
         np_odt = np.float64 if args.precision == 'fp64' else np.float32
         call_rate = call_rate_pageable = None
         if n_e2e:
@@ -543,51 +698,58 @@ def gpu_arm(args, rank, world, local_rank):
                'calc_flow_call_value': call_rate,
                'calc_flow_call_api': 'calc_flow%dD(host ndarray window) -> host ndarrays (pinned), rank 0' % ndim,
                'calc_flow_call_plain_numpy_value': call_rate_pageable}
+        if n_e2e:
+            del hfr
+    del frames
+    m['frames'] = None
+    torch.cuda.empty_cache()
+
+    # ---- z-slab sharding (BASELINE config 5), scaled to the ranks present: 64 owned planes of 2048x2048 per rank -- the
+    # slab of config 5 at 8 GPUs, where this IS config 5 -- so that every multi-GPU line carries a measured z-slab record
+    zrec = None
+    if world > 1 and not args.no_zslab and args.workload == 'cfg4':
+        w5 = WORKLOADS['cfg5']
+        zrec = zslab_measure(rank, world, local_rank, w5['sig'], 64 * world, w5['shape'][2], w5['shape'][3], args.precision, 2, 1,
+                             args.chunk_planes)
+
+    # ---- the other BASELINE configs, device-timed on a few timepoints each (single-GPU runs)
+    configs = None
+    if world == 1 and not args.no_configs and args.workload == 'cfg4' and args.timepoints is None and not args.generic:
+        configs = []
+        for wl, prc, tps, stp in (('cfg1', 'fp64', 1, 50), ('cfg2', 'fp64', 25, 3), ('cfg3', 'fp64', 6, 3), ('cfg3', 'fp32', 6, 3),
+                                  ('cfg4', 'fp32', 4, 2)):
+            mm = device_measure(ctx, local_rank, 0, 1, wl, prc, tps, stp, 3)
+            mm['frames'] = None
+            torch.cuda.empty_cache()
+            v = mm['n_out'] * mm['vol'] * stp / (mm['ms'] * 1e-3)
+            rr = roofline_record(mm, wl, prc, v, 1, stp, False)
+            configs.append({'workload': wl, 'metric': METRICS[wl], 'dtype': 'f64' if prc == 'fp64' else 'f32', 'value': v, 'unit': UNIT,
+                            'shape': [mm['nt']] + list(mm['sp']), 'sigmas': list(mm['sig']), 'timepoints_per_step': mm['n_out'],
+                            'steps': stp, 'ms_per_timepoint': mm['ms'] / (stp * mm['n_out']),
+                            'api': ('of3d_flow2d_batch, %d timepoints per launch set' % mm['batch2d']) if mm['batch2d'] else 'of3d_flow_frames',
+                            'hbm_frac': rr['pipeline']['hbm_frac'], 'fp_frac': rr['pipeline']['fp_frac'],
+                            'alg_bytes_per_voxel': rr['pipeline']['alg_bytes_per_voxel'], 'alg_fma_per_voxel': rr['pipeline']['alg_fma_per_voxel'],
+                            'stages_ms': {r['stage']: round(r['ms_per_timepoint'], 4) for r in rr['stages']}})
 
     if rank != 0:
         return
-    peak, peak_src = peaks()
-    bpv = alg_bytes_per_voxel(sig, ndim, args.precision)
-    ach = value * bpv / 1e9 / world                             # per-GPU algorithmic GB/s
-    fma = alg_fma_per_voxel(sig, ndim)
-    fpk = fma_peak(args.precision)
-    tr = measured_traffic(args.workload, args.precision)
-    # roofline of the DOMINANT kernel, timed live by the library's event brackets on its own stream during the timed
-    # region (rank 0); the whole-pipeline figures (window read once, outputs written once) ride along
-    pipeline = {'alg_bytes_per_voxel': bpv, 'alg_gbs': ach, 'hbm_frac': ach / peak,
-                'traffic_bytes_per_voxel': (tr['bytes_per_voxel'] if tr else None),
-                'alg_fma_per_voxel': fma, 'tfma_per_s': value * fma / 1e12 / world,
-                'fp_frac': (value * fma / 1e12 / world / fpk) if fpk else None,
-                'launch': 'one output timepoint = %s kernels' % (tr['kernels'] if tr else 'several')}
-    rows = stage_report(stages, stage_model(sig, ndim, args.precision), vol, len(mine) * args.steps, peak, fpk)
-    top = next((r for r in rows if 'alg_gbs' in r), None)
-    if top:
-        full = args.shape is None and args.timepoints is None and not args.generic
-        sd = (tr or {}).get('stage_dram_bytes_per_launch', {}) if full else {}
-        roof = {'bound': 'hbm', 'kernel': top['stage'], 'achieved': top['alg_gbs'], 'peak': peak, 'unit': 'GB/s',
-                'frac': top['hbm_frac'], 'traffic': sd.get(top['stage']), 'peak_source': peak_src,
-                'alg_bytes_per_voxel': top['alg_bytes_per_voxel'], 'alg_bytes_per_launch': top['alg_bytes_per_voxel'] * vol,
-                'launch_ms': top['ms_per_timepoint'], 'share_of_step': top['ms_per_timepoint'] * len(mine) * args.steps / ms,
-                'fp_pipe': {'alg_fma_per_voxel': top['alg_fma_per_voxel'], 'achieved_tfma_per_s': top['tfma_per_s'],
-                            'peak_tfma_per_s': fpk, 'frac': top['fp_frac'],
-                            'note': 'the roof that binds this kernel is the CUDA-core FMA pipe (measured peak, '
-                                    'tools/fma_peak.cu), not HBM; see DESIGN.md 3.3'},
-                'stages': rows, 'pipeline': pipeline}
-    else:                                                        # generic kernels / stage events disabled
-        roof = {'bound': 'hbm', 'kernel': 'whole pipeline', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                'traffic': (tr['bytes_per_voxel'] * vol if tr else None), 'peak_source': peak_src,
-                'alg_bytes_per_voxel': bpv, 'alg_bytes_per_launch': bpv * vol, 'stages': rows, 'pipeline': pipeline}
+    full = args.shape is None and args.timepoints is None and not args.generic
+    roof = roofline_record(m, args.workload, args.precision, value, world, args.steps, full)
     line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'metric': METRICS[args.workload], 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f64' if args.precision == 'fp64' else 'f32', 'data': 'synthetic',
         'config': {'workload': args.workload, 'shape': [nt] + list(sp), 'sigmas': list(sig), 'input_dtype': 'uint16',
-                   'output_timepoints_per_step': len(outs_all), 'sharding': 'output timepoint, no collective',
+                   'output_timepoints_per_step': m['n_out'], 'sharding': 'output timepoint, no collective',
                    'l2': 'inputs+intermediates per timepoint (>= %.1f GB) exceed the 126 MB L2' % (kt * vol * 2 / 1e9),
                    'kernels': 'generic' if args.generic else 'default'},
         'roofline': roof,
         'clocks': clocks, 'gpu_launches': int(lsum.item()), 'e2e': e2e,
     }
+    if zrec is not None:
+        line['zslab'] = zrec
+    if configs is not None:
+        line['configs'] = configs
     if world == 1 and not args.no_cpu_baseline:
         v, _, sample = run_cpu(args.workload, 1, 1, 0, args.cpu_voxels * 4)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': cpu_kind(), 'sample': sample}
@@ -616,7 +778,10 @@ def main():
     ap.add_argument('--no-stage-events', action='store_true', help='do not bracket the launches with CUDA events')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-voxels', type=int, default=400_000, help='voxels per core per CPU step')
-    ap.add_argument('--cpu-cores', type=int, default=None)
+    ap.add_argument('--cpu-cores', type=int, default=None, help='processes of the CPU arm (default 16, or all cores if fewer)')
+    ap.add_argument('--chunk-planes', type=int, default=64, help='z-slab runs: owned planes per pass of the slab pipeline')
+    ap.add_argument('--no-zslab', action='store_true', help='multi-GPU runs: skip the z-slab sub-record')
+    ap.add_argument('--no-configs', action='store_true', help='single-GPU runs: skip the quick lines of the other BASELINE configs')
     ap.add_argument('--shape', default=None, help='override the workload shape, e.g. 19,128,512,512 (debug)')
     args = ap.parse_args()
     if args.shape:

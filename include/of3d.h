@@ -134,6 +134,16 @@ OF3D_API int of3d_flow_frames(of3d_ctx* ctx, int ndim, const void* const* frames
                      void* vx, void* vy, void* vz, void* rel, int out_mem);
 
 /*
+ * calc_flow2D of `n_out` CONSECUTIVE output timepoints of a 2D time-lapse in one call (the loop of calc_flow.py:599-606):
+ * frames[i], i < n_out + nT - 1, are consecutive DEVICE frames; output timepoint j is the centre of frames[j .. j+nT-1];
+ * vx, vy, rel are DEVICE buffers (n_out, ny, nx).  The temporal stage runs per timepoint, every later stage once over all
+ * n_out planes -- a single 2048x2048 frame does not fill the 148 SMs for more than a wave or two per launch.  Results are
+ * identical to n_out separate of3d_flow_frames calls.  n_out + nT - 1 <= 129.
+ */
+OF3D_API int of3d_flow2d_batch(of3d_ctx* ctx, const void* const* frames, int in_dtype, int64_t n_out, int64_t ny, int64_t nx,
+                               const of3d_taps* taps, int precision, unsigned flags, void* vx, void* vy, void* rel);
+
+/*
  * The synchronous host-to-host call (calc_flow3D(ndarray) -> ndarrays), pipelined.  of3d_window_upload copies `bytes`
  * bytes at byte `offset` of frame k (of n_frames, frame_bytes each) from page-locked host memory into a device-resident
  * window on a dedicated copy stream and returns at once, so that the caller can prepare (stage, convert) the next piece

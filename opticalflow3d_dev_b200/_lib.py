@@ -40,6 +40,7 @@ SIGNATURES = {
     'of3d_flow2d': (_i, [_vp, _vp, _i, _i, _i64, _i64, _i64, C.POINTER(Taps), _i, _u, _vp, _vp, _vp, _i]),
     'of3d_flow_frames': (_i, [_vp, _i, C.POINTER(_vp), _i, _i, _i64, _i64, _i64, C.POINTER(Taps), _i, _u,
                               _vp, _vp, _vp, _vp, _i]),
+    'of3d_flow2d_batch': (_i, [_vp, C.POINTER(_vp), _i, _i64, _i64, _i64, C.POINTER(Taps), _i, _u, _vp, _vp, _vp]),
     'of3d_temporal': (_i, [_vp, _i, C.POINTER(_vp), _i, _i, _i64, _i64, _i64, C.POINTER(Taps), _i, _u, _vp, _vp]),
     'of3d_flow_from_dt': (_i, [_vp, _i, _vp, _vp, _i64, _i64, _i64, C.POINTER(Taps), _i, _u, _vp, _vp, _vp, _vp, _i]),
     'of3d_comm_unique_id': (_i, [_vp]),

@@ -24,7 +24,7 @@ import numpy as np
 from . import _lib
 from .taps import flow_taps
 
-__all__ = ['calc_flow2D', 'calc_flow3D', 'process_flow']
+__all__ = ['calc_flow2D', 'calc_flow3D', 'calc_flow2D_timelapse', 'process_flow']
 
 _MSG_NDIM_2D = 'ERROR: Input image must be a 3D matrix with dimensions N_T, N_Y, N_X'
 _MSG_NDIM_3D = 'ERROR: Input image must be a 3D matrix with dimensions N_T, N_Z, N_Y, N_X'
@@ -239,6 +239,57 @@ def calc_flow3D(images, xyzSig=3, tSig=1, wSig=4, *, precision='fp64', device=No
     vx, vy, vz, rel = _run(images, xyzSig, tSig, wSig, 3, precision, device, exact, generic, out,
                            rel_f32=(rel_dtype == 'reference'))
     return vx, vy, vz, rel
+
+
+def calc_flow2D_timelapse(images, xySig=3, tSig=1, wSig=4, *, precision='fp64', device=None, batch=16):
+    """
+    calc_flow2D of EVERY analysable frame of a 2D time-lapse ``images`` (N_T, N_Y, N_X): what the reference's loop over
+    windows (calc_flow.py:599-606) computes one window at a time.  Returns (vx, vy, rel), each (N_T - 2R, N_Y, N_X) with
+    R = ceil(3*tSig); row j belongs to frame j + R.  The frames are uploaded once and processed `batch` timepoints per
+    launch set (of3d_flow2d_batch): identical values to per-window calc_flow2D calls, at about twice the rate on
+    2048x2048 frames.  NumPy in -> NumPy out; CUDA tensor in -> CUDA tensors out.
+    """
+    if not (len(images.shape) == 3):
+        sys.exit(_MSG_NDIM_2D)
+    tp = flow_taps(xySig, tSig, wSig)
+    taps, keep = _lib.make_taps(tp)
+    kt = keep[3].size
+    nt, ny, nx = (int(v) for v in images.shape)
+    if nt < 6 * tSig + 1 or nt < kt:
+        sys.exit(_MSG_SHORT)
+    import torch
+    cuda_in = _is_cuda_tensor(images)
+    if cuda_in:
+        dev = images.device.index if device is None else int(device)
+        fr = images.contiguous()
+    else:
+        dev = _default_device() if device is None else int(device)
+        a = np.ascontiguousarray(images, dtype=_device_dtype(np.asarray(images).dtype))
+        fr = torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else (a.view(np.int32) if a.dtype == np.uint32 else a)).cuda(dev)
+        np_dt = a.dtype
+    if cuda_in:
+        np_dt = np.dtype(str(fr.dtype).replace('torch.', ''))
+    if np_dt not in _lib.DTYPE_CODES:
+        raise TypeError('calc_flow: unsupported image dtype %s' % np_dt)
+    ctx = _lib.get_context(dev)
+    n_out = nt - kt + 1
+    odt = torch.float64 if precision == 'fp64' else torch.float32
+    outs = [torch.empty((n_out, ny, nx), dtype=odt, device=fr.device) for _ in range(3)]
+    fb = ny * nx * fr.element_size()
+    plane_o = ny * nx * outs[0].element_size()
+    torch.cuda.current_stream(dev).synchronize()
+    bmax = max(1, min(int(batch), 129 - kt + 1))
+    for j0 in range(0, n_out, bmax):
+        b = min(bmax, n_out - j0)
+        ptrs = (C.c_void_p * (b + kt - 1))(*[fr.data_ptr() + (j0 + i) * fb for i in range(b + kt - 1)])
+        rc = ctx.lib.of3d_flow2d_batch(ctx.handle, ptrs, _lib.DTYPE_CODES[np_dt], b, ny, nx, C.byref(taps),
+                                       _lib.FP64 if precision == 'fp64' else _lib.FP32, 0,
+                                       *[C.c_void_p(o.data_ptr() + j0 * plane_o) for o in outs])
+        _lib.check(rc, 'of3d_flow2d_batch')
+    ctx.sync()
+    if cuda_in:
+        return tuple(outs)
+    return tuple(o.cpu().numpy() for o in outs)
 
 
 def process_flow(imDir, imName, fileType="SequenceT", spatialDimensions=3, xyzSig=3, tSig=1, wSig=4, **kwargs):

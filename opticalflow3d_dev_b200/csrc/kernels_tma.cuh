@@ -100,8 +100,8 @@ __device__ __noinline__ void window_tma_producer(const CUtensorMap* tm8, const C
 }
 
 // tensor maps: {x, y, 4 volumes, z} over the gradient volumes {dt, dx, dy, dz}
-template <typename T, int K, int P, int NG>
-__global__ void __launch_bounds__((9 * NG + 1) * 32, 1) march_window_tma(const WindowArgs<T, K> a, const __grid_constant__ CUtensorMap tm8,
+template <typename T, int K, int P, int NG, int MINB = 1>
+__global__ void __launch_bounds__((9 * NG + 1) * 32, MINB) march_window_tma(const WindowArgs<T, K> a, const __grid_constant__ CUtensorMap tm8,
                                                                           const __grid_constant__ CUtensorMap tm1) {
     static_assert(P >= K && P % kTmaZT == 0, "bad unroll period");
     constexpr int R = K / 2, ZT = kTmaZT, ST = kTmaStages, TX = 32 * NG;

@@ -292,7 +292,13 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
     if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
     if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3"); return OF3D_ERR_ARG; }
     if (int rc = check_taps(t)) return rc;
-    if (nz < 1 || ny < 1 || nx < 1 || (ndim == 2 && nz != 1)) { set_error("bad volume shape"); return OF3D_ERR_ARG; }
+    // ndim == 2 with nz > 1: a BATCH of nz consecutive output timepoints of a 2D time-lapse (of3d_flow2d_batch): `frames`
+    // holds nz + nT - 1 consecutive device frames and the outputs are (nz, ny, nx)
+    const bool batch2d = ndim == 2 && nz > 1;
+    if (nz < 1 || ny < 1 || nx < 1) { set_error("bad volume shape"); return OF3D_ERR_ARG; }
+    if (batch2d && (stage != 0 || in_mem != OF3D_DEVICE || out_mem != OF3D_DEVICE || own_n != 0)) { set_error("2D batches take device frames and device outputs"); return OF3D_ERR_ARG; }
+    const int n_frames = stage == 2 ? 0 : (batch2d ? (int)nz + t->nT - 1 : t->nT);
+    if (n_frames > kMaxFrames) { set_error("too many frames in one 2D batch"); return OF3D_ERR_ARG; }
     if (own_n == 0) { own_lo = 0; own_n = nz; }
     if (own_lo < 0 || own_n < 1 || own_lo + own_n > nz) { set_error("bad z range"); return OF3D_ERR_ARG; }
     if (precision != OF3D_FP64 && precision != OF3D_FP32) { set_error("precision must be OF3D_FP64 or OF3D_FP32"); return OF3D_ERR_ARG; }
@@ -300,7 +306,7 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
     if (stage != 2) {
         if (!dtype_size(in_dtype)) { set_error("unsupported input dtype"); return OF3D_ERR_ARG; }
         if (!frames) { set_error("null image pointer"); return OF3D_ERR_ARG; }
-        for (int k = 0; k < t->nT; ++k) if (!frames[k]) { set_error("null frame pointer"); return OF3D_ERR_ARG; }
+        for (int k = 0; k < n_frames; ++k) if (!frames[k]) { set_error("null frame pointer"); return OF3D_ERR_ARG; }
     }
     if (stage != 0 && (!ic_dev || !dt0_dev)) { set_error("null ic/dt0 pointer"); return OF3D_ERR_ARG; }
     const bool rel_f32 = stage != 1 && precision == OF3D_FP64 && (flags & OF3D_FLAG_REL_F32);
@@ -316,7 +322,7 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
         for (const void* q : chk)
             if (q && reinterpret_cast<uintptr_t>(q) % al) { set_error("device buffers must be aligned to the compute type"); return OF3D_ERR_ARG; }
         if (stage != 2 && in_mem == OF3D_DEVICE)
-            for (int k = 0; k < t->nT; ++k)
+            for (int k = 0; k < n_frames; ++k)
                 if (reinterpret_cast<uintptr_t>(frames[k]) % dtype_size(in_dtype)) { set_error("frame pointers must be aligned to the image dtype"); return OF3D_ERR_ARG; }
     }
     if (stage != 1 && (!vx || !vy || !rel || (ndim == 3 && !vz))) { set_error("null image or output pointer"); return OF3D_ERR_ARG; }
@@ -351,8 +357,34 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
                 fp.p[k] = d;
             }
         } else {
-            for (int k = 0; k < t->nT; ++k) fp.p[k] = frames[k];
+            for (int k = 0; k < n_frames; ++k) fp.p[k] = frames[k];
         }
+    }
+    if (batch2d) {
+        // temporal stage plane by plane (every output timepoint has its own window of frames), then the spatial stages
+        // of all nz planes in ONE set of launches: whole waves instead of five launch tails per frame
+        char* ic = ws_take<char>(c, (size_t)n * ts);
+        char* dt0 = ws_take<char>(c, (size_t)n * ts);
+        const Shape s1{2, 1, ny, nx};
+        void* none[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int64_t j = 0; j < nz; ++j) {
+            FramePtrs fj;
+            memset(&fj, 0, sizeof(fj));
+            for (int k = 0; k < t->nT; ++k) fj.p[k] = fp.p[j + k];
+            void* icj = ic + (size_t)j * ny * nx * ts; void* dtj = dt0 + (size_t)j * ny * nx * ts;
+            const int rc = precision == OF3D_FP64
+                ? run_typed<double>(c, s1, &fj, in_dtype, t, flags, nullptr, nullptr, icj, dtj, false, 0, 1, none, false)
+                : run_typed<float>(c, s1, &fj, in_dtype, t, flags, nullptr, nullptr, icj, dtj, false, 0, 1, none, false);
+            if (rc) return rc;
+        }
+        void* dout2[4] = {vx, vy, nullptr, rel};
+        const int rc = precision == OF3D_FP64
+            ? run_typed<double>(c, s, nullptr, in_dtype, t, flags, ic, dt0, nullptr, nullptr, true, 0, nz, dout2, false)
+            : run_typed<float>(c, s, nullptr, in_dtype, t, flags, ic, dt0, nullptr, nullptr, true, 0, nz, dout2, false);
+        if (rc) return rc;
+        OF3D_CUDA_TRY(cudaGetLastError());
+        if (!c->async) OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return OF3D_OK;
     }
     void* out[4] = {vx, vy, vz, rel};
     void* dout[4] = {vx, vy, vz, rel};
@@ -521,6 +553,11 @@ OF3D_API int of3d_flow3d(of3d_ctx* ctx, const void* images, int in_dtype, int in
 OF3D_API int of3d_flow2d(of3d_ctx* ctx, const void* images, int in_dtype, int in_mem, int64_t nt, int64_t ny, int64_t nx,
                 const of3d_taps* taps, int precision, unsigned flags, void* vx, void* vy, void* rel, int out_mem) {
     return flow_contig(ctx, 2, images, in_dtype, in_mem, nt, 1, ny, nx, taps, precision, flags, vx, vy, nullptr, rel, out_mem);
+}
+
+OF3D_API int of3d_flow2d_batch(of3d_ctx* ctx, const void* const* frames, int in_dtype, int64_t n_out, int64_t ny, int64_t nx,
+                               const of3d_taps* taps, int precision, unsigned flags, void* vx, void* vy, void* rel) {
+    return flow_staged(ctx, 0, 2, frames, in_dtype, OF3D_DEVICE, n_out, ny, nx, taps, precision, flags, nullptr, nullptr, vx, vy, nullptr, rel, OF3D_DEVICE);
 }
 
 OF3D_API int of3d_flow_frames(of3d_ctx* ctx, int ndim, const void* const* frames, int in_dtype, int in_mem, int64_t nz, int64_t ny,

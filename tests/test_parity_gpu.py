@@ -292,6 +292,35 @@ def test_full_size_fast_path_matches_generic_kernels(shape, sig, ndim):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize('shape,sig,precision,dtype', [
+    ((12, 70, 96), (1.5, 1, 4), 'fp64', np.uint16),
+    ((16, 33, 41), (1, 2, 2), 'fp64', np.float32),          # 13 temporal taps, odd rows
+    ((11, 64, 64), (3, 1, 4), 'fp32', np.uint8),
+])
+def test_flow2d_batch_equals_per_window_calls(shape, sig, precision, dtype):
+    """calc_flow2D_timelapse (of3d_flow2d_batch: temporal stage per timepoint, every later stage once over the batch)
+    returns exactly what calc_flow2D returns window by window -- and so matches the oracle."""
+    from opticalflow3d_dev_b200.synth import make_stack
+    cf = _cf()
+    img = make_stack(shape, seed=61, dtype=np.uint16).astype(dtype)
+    kt = 2 * int(np.ceil(3 * sig[1])) + 1
+    got = cf.calc_flow2D_timelapse(img, *sig, precision=precision, batch=4)
+    n_out = shape[0] - kt + 1
+    assert all(g.shape == (n_out,) + shape[1:] for g in got)
+    for j in range(n_out):
+        ref = cf.calc_flow2D(img[j:j + kt], *sig, precision=precision)
+        for g, r in zip(got, ref):
+            assert np.array_equal(g[j], r, equal_nan=True), j
+    if precision == 'fp64':
+        ref = orc.lk_flow2d(img[1:1 + kt], *sig)
+        assert_flow_close([g[1] for g in got[:2]], ref[:2], ref[2], 1e-9, 'batch2d')
+    import torch
+    t = cf.calc_flow2D_timelapse(torch.from_numpy(img.astype(np.float32)).cuda(), *sig, precision=precision, batch=64)
+    assert t[0].is_cuda and t[0].shape[0] == n_out
+    with pytest.raises(SystemExit):
+        cf.calc_flow2D_timelapse(img[:kt - 1], *sig)
+
+
 def test_tap_counts_without_specialised_kernels_fall_back_to_generic():
     """wSig = 9 -> 55 window taps, xyzSig = 5 -> 31 gradient taps: no marching/strip instantiation; the generic
     kernels must take over transparently and still match the oracle."""

@@ -198,7 +198,7 @@ def test_caller_supplied_stream():
         assert ctx.stream == s.cuda_stream
         ctx.set_async(True)
         with torch.cuda.stream(s):
-            dev = torch.from_numpy(img).cuda(non_blocking=True) + 0        # produced on s, consumed by the library on s
+            dev = torch.from_numpy(img).cuda(non_blocking=True).clone()   # produced on s, consumed by the library on s
             got = calc_flow3D(dev, 1, 1, 2, rel_dtype='float64')
             tot = [g.sum() for g in got]                                      # torch work after the call, same stream
         s.synchronize()
