@@ -172,7 +172,7 @@ def get_context(device=None):
 # Plain NumPy arrays are pageable: copying a 1024x1024x128 result (3.8 GB) into freshly allocated pageable memory takes
 # ~700 ms, into pinned memory 67 ms.  Pinned blocks are expensive to create (the pages are locked one by one), so the
 # blocks of dead arrays are kept in a size-keyed pool and handed out again.
-_POOL_LOCK = threading.Lock()
+_POOL_LOCK = threading.RLock()      # re-entrant: a finaliser (_release_block) may run inside a locked region during GC
 _POOL = {}                       # rounded size -> [address, ...] of free blocks
 _POOL_BYTES = 0
 _RANGES = {}                     # address -> size of every live pinned block (pooled or in use)
@@ -181,6 +181,19 @@ _POOL_GRAIN = 2 << 20
 
 def _pool_cap():
     return int(float(os.environ.get('OF3D_PINNED_POOL_GB', '24')) * (1 << 30))
+
+
+def _live_cap():
+    """Upper bound on page-locked host memory handed out to callers and the pool together ($OF3D_PINNED_MAX_GB, default
+    half of the physical RAM): beyond it pinned_empty(pooled=True) raises and the callers fall back to pageable arrays,
+    so a script that keeps many results alive cannot pin the whole machine."""
+    env = os.environ.get('OF3D_PINNED_MAX_GB')
+    if env is not None:
+        return int(float(env) * (1 << 30))
+    try:
+        return os.sysconf('SC_PAGE_SIZE') * os.sysconf('SC_PHYS_PAGES') // 2
+    except (ValueError, OSError):
+        return 64 << 30
 
 
 def _release_block(addr, size, pooled):
@@ -215,6 +228,11 @@ def pinned_empty(shape, dtype, pooled=False):
                 addr = free.pop()
                 _POOL_BYTES -= size
     if addr is None:
+        if pooled:
+            with _POOL_LOCK:
+                live = sum(_RANGES.values())
+            if live + size > _live_cap():
+                raise RuntimeError('page-locked host memory cap reached (%d bytes live; OF3D_PINNED_MAX_GB)' % live)
         p = C.c_void_p()
         check(lib.of3d_host_alloc(C.byref(p), size), 'of3d_host_alloc')
         addr = p.value

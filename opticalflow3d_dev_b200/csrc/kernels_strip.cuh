@@ -387,8 +387,8 @@ __device__ __forceinline__ void solve_unit_voxels(const T* park, int parkrow, in
     }
 }
 
-template <typename T, int K, int P, int NCH, int NHALF, bool PROD, int MINB = 1>
-__global__ void __launch_bounds__(NCH * NHALF * 32, MINB) strip_window_solve(const StripArgs<T, K> a) {
+template <typename T, int K, int P, int NCH, int NHALF, bool PROD>
+__global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const StripArgs<T, K> a) {
     constexpr int RB = kStripRB, R = K / 2, TX = 32 * NHALF;
     constexpr int PARKROW = strip_parkrow<NCH, NHALF>();
     static_assert(P >= K && P % RB == 0, "unroll period must cover the taps and be a multiple of the batch");

@@ -16,12 +16,15 @@ struct Flow2 { double vx, vy, rel; };
 // Branch-free double-precision reciprocal and reciprocal square root: hardware seed (MUFU.RCP64H / RSQ64H,
 // 20 mantissa bits, full exponent range) plus two Newton steps -> ~1 ulp.  No slow-path branch, so several
 // voxels' dependency chains can be interleaved by the compiler (the IEEE division's fix-up branch prevents that).
+// Special values: the Newton steps would turn the seed of 0 / denormal (inf) or of inf / huge (0) into NaN; outside
+// [DBL_MIN, 1e300] the seed itself is returned (+-inf resp. +-0, what the reference's `**-1` gives up to the denormals).
 __device__ __forceinline__ double rcp_fast(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double s;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x));
+    double r = fma(fma(-x, s, 1.0), s, s);
     r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
-    return r;
+    const double ax = fabs(x);
+    return (ax >= 2.2250738585072014e-308 && ax <= 1e300) ? r : s;
 }
 __device__ __forceinline__ double rsqrt_fast(double x) {
     double y;
@@ -54,7 +57,9 @@ __device__ __forceinline__ double min_eig_sym3(double xx, double xy, double xz, 
     const double a = xx - q, b = yy - q, c = zz - q;
     const double p1 = xy * xy + xz * xz + yz * yz;
     const double p2 = (a * a + b * b + c * c + 2.0 * p1) * (1.0 / 6.0);
-    const bool scalar = !(p2 > 0.0);                 // scalar matrix (incl. all-zero): every eigenvalue is q
+    // scalar matrix (incl. all-zero): every eigenvalue is q.  Also taken below 1e-280, where rsqrt.approx.ftz would see a
+    // denormal: the eigenvalues then differ from q by less than 1e-139
+    const bool scalar = !(p2 > 1e-280);
     const double ip = rsqrt_fast(scalar ? 1.0 : p2);
     const double p = p2 * ip;
     const double ba = a * ip, bb = b * ip, bc = c * ip, bxy = xy * ip, bxz = xz * ip, byz = yz * ip;
