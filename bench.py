@@ -302,7 +302,7 @@ def reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, steps, warmup, chunk_planes, seed=1005):
+def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, steps, warmup, chunk_planes, seed=1005, mode='dt'):
     """ONE output timepoint of a (kt, nz_total, ny, nx) uint16 window sharded by z-slab over the ranks of the default
     process group: every step = in-library NCCL halo exchange of the raw frames (straight into each rank's extended
     buffer, asynchronous) + of3d_flow3d_slab on the owned planes (chunks that do not touch a halo run during the
@@ -330,7 +330,8 @@ def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, ste
     # ---- (b) parity on a small volume: sharded == unsharded, bit for bit
     H = multigpu.halo_planes(sig[0], sig[2])
     pn = (H + 7) * world
-    small = multigpu.ZSlab(pn, 96, 128, np.uint16, sig, precision=precision, device=local_rank, chunk_planes=16, rel_dtype='float64')
+    small = multigpu.ZSlab(pn, 96, 128, np.uint16, sig, precision=precision, device=local_rank, chunk_planes=16, rel_dtype='float64',
+                           exchange=mode)
     fill(small, small.z0, pn)
     small.exchange()
     part = small.flow()
@@ -353,7 +354,7 @@ def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, ste
 
     # ---- the measured volume
     zs_ = multigpu.ZSlab(nz_total, ny, nx, np.uint16, sig, precision=precision, device=local_rank, chunk_planes=chunk_planes,
-                         rel_dtype='float64')
+                         rel_dtype='float64', exchange=mode)
     tmp = fill(zs_, zs_.z0, nz_total)
     outs = None
 
@@ -366,20 +367,22 @@ def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, ste
 
     outs = list(step())
     ctx.sync()
-    # ---- (a) the halo planes that arrived are the neighbour's planes
+    # ---- (a) the halo planes that arrived are the neighbour's planes (dt mode: the widened centre frame in `ic`)
     halo_ok = True
+    kc = zs_.kt // 2
+
+    def check_halo(z_first, count, got_raw, got_ic, t_raw):
+        chk = torch.empty((count, ny, nx), dtype=torch.uint16, device=dev)
+        torch.cuda.synchronize()
+        _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, chk.data_ptr(), 1, count, ny, nx, kc if mode == 'dt' else t_raw, z_first, seed), 'synth')
+        return bool(torch.equal(chk.to(got_ic.dtype), got_ic)) if mode == 'dt' else bool(torch.equal(chk, got_raw))
+
     if zs_.lo:
-        chk = torch.empty((zs_.lo, ny, nx), dtype=torch.uint16, device=dev)
-        torch.cuda.synchronize()
-        _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, chk.data_ptr(), 1, zs_.lo, ny, nx, zs_.kt - 1, zs_.z0 - zs_.lo, seed), 'synth')
-        halo_ok = halo_ok and bool(torch.equal(chk, zs_.frames[zs_.kt - 1, :zs_.lo]))
-        del chk
+        halo_ok = halo_ok and check_halo(zs_.z0 - zs_.lo, zs_.lo, None if mode == 'dt' else zs_.frames[zs_.kt - 1, :zs_.lo],
+                                         zs_.ic[:zs_.lo] if mode == 'dt' else None, zs_.kt - 1)
     if zs_.hi:
-        chk = torch.empty((zs_.hi, ny, nx), dtype=torch.uint16, device=dev)
-        torch.cuda.synchronize()
-        _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, chk.data_ptr(), 1, zs_.hi, ny, nx, 0, zs_.z1, seed), 'synth')
-        halo_ok = halo_ok and bool(torch.equal(chk, zs_.frames[0, zs_.lo + zs_.own:]))
-        del chk
+        halo_ok = halo_ok and check_halo(zs_.z1, zs_.hi, None if mode == 'dt' else zs_.frames[0, zs_.lo + zs_.own:],
+                                         zs_.ic[zs_.lo + zs_.own:] if mode == 'dt' else None, 0)
     del tmp
     for _ in range(max(warmup - 1, 0)):
         step()
@@ -419,9 +422,13 @@ def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, ste
         'dtype': 'f64' if precision == 'fp64' else 'f32',
         'config': {'shape': [kt, nz_total, ny, nx], 'sigmas': list(sig), 'input_dtype': 'uint16', 'planes_per_rank': nz_total // world,
                    'chunk_planes': chunk_planes,
-                   'sharding': 'z-slab; %d raw halo planes of each of the %d frames exchanged with each neighbour by the '
-                               'library (grouped ncclSend/ncclRecv, in place); interior chunks overlap the exchange' % (H, kt),
-                   'halo_bytes_per_rank_per_step': int(2 * H * kt * ny * nx * es)},
+                   'exchange': mode,
+                   'sharding': ('z-slab; temporal stage on the boundary planes, then %d halo planes of (ic, dt0) exchanged with each '
+                                'neighbour by the library (grouped ncclSend/ncclRecv, in place) while the interior temporal stage '
+                                'runs; interior chunks overlap the exchange' % H) if mode == 'dt' else
+                               ('z-slab; %d raw halo planes of each of the %d frames exchanged with each neighbour by the '
+                                'library (grouped ncclSend/ncclRecv, in place); interior chunks overlap the exchange' % (H, kt)),
+                   'halo_bytes_sent_per_interior_rank_per_step': int(2 * H * ny * nx * (2 * (8 if precision == 'fp64' else 4) if mode == 'dt' else kt * es))},
         'parity_small_volume_bit_identical': parity, 'halo_planes_verified': bool(stat[2].item() == 0.0),
         'free_hbm_bytes_rank0_after': int(mem[0]),
         'roofline': {'bound': 'hbm', 'achieved': value * bpv / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
@@ -449,7 +456,8 @@ def zslab_arm(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    rec = zslab_measure(rank, world, local_rank, w['sig'], nz, ny, nx, args.precision, args.steps, args.warmup, args.chunk_planes)
+    rec = zslab_measure(rank, world, local_rank, w['sig'], nz, ny, nx, args.precision, args.steps, args.warmup, args.chunk_planes,
+                        mode=args.zslab_exchange)
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         line = dict(rec)
@@ -710,7 +718,7 @@ def gpu_arm(args, rank, world, local_rank):
     if world > 1 and not args.no_zslab and args.workload == 'cfg4':
         w5 = WORKLOADS['cfg5']
         zrec = zslab_measure(rank, world, local_rank, w5['sig'], 64 * world, w5['shape'][2], w5['shape'][3], args.precision, 2, 1,
-                             args.chunk_planes)
+                             args.chunk_planes, mode=args.zslab_exchange)
 
     # ---- the other BASELINE configs, device-timed on a few timepoints each (single-GPU runs)
     configs = None
@@ -780,6 +788,7 @@ def main():
     ap.add_argument('--cpu-voxels', type=int, default=400_000, help='voxels per core per CPU step')
     ap.add_argument('--cpu-cores', type=int, default=None, help='processes of the CPU arm (default 16, or all cores if fewer)')
     ap.add_argument('--chunk-planes', type=int, default=64, help='z-slab runs: owned planes per pass of the slab pipeline')
+    ap.add_argument('--zslab-exchange', default='dt', choices=['dt', 'raw'], help="halo exchange of (ic, dt0) or of the raw frames")
     ap.add_argument('--no-zslab', action='store_true', help='multi-GPU runs: skip the z-slab sub-record')
     ap.add_argument('--no-configs', action='store_true', help='single-GPU runs: skip the quick lines of the other BASELINE configs')
     ap.add_argument('--shape', default=None, help='override the workload shape, e.g. 19,128,512,512 (debug)')

@@ -200,6 +200,12 @@ OF3D_API int of3d_flow_from_dt(of3d_ctx* ctx, int ndim, const void* ic_dev, cons
  *       owned range needs (gradients on own +- Rw, window sums and solve on own).  chunk_planes > 0 works through the
  *       owned range in chunks of that many planes (interior chunks first, overlapping the exchange), which bounds the
  *       workspace by the chunk instead of the slab; 0 = one chunk.  Results are bit-identical to the unsharded call.
+ *   of3d_flow3d_slab_dt
+ *       the same on extended (ic, dt0) DEVICE volumes of the compute type (of3d_temporal's outputs): a rank runs the
+ *       temporal stage on its boundary planes, starts the exchange of those two volumes' halo planes -- 16 (8 in fp32)
+ *       bytes per voxel instead of 2 nT, a quarter of the raw frames' halo at nT = 19 -- and runs the temporal stage of
+ *       its interior planes while the halos travel.  For 8/16-bit integer frames the temporal kernels use the arithmetic
+ *       of the fused z march, so this path, too, is bit-identical to the unsharded call.
  */
 OF3D_API int of3d_comm_unique_id(void* id128);
 OF3D_API int of3d_comm_init(of3d_ctx* ctx, const void* id128, int nranks, int rank);
@@ -209,6 +215,9 @@ OF3D_API int of3d_halo_exchange(of3d_ctx* ctx, void* const* frames_ext, int n_fr
 OF3D_API int of3d_flow3d_slab(of3d_ctx* ctx, const void* const* frames_ext, int in_dtype, int64_t nz_ext, int64_t ny, int64_t nx,
                               int64_t own_lo, int64_t own_n, int64_t chunk_planes, const of3d_taps* taps, int precision,
                               unsigned flags, void* vx, void* vy, void* vz, void* rel);
+OF3D_API int of3d_flow3d_slab_dt(of3d_ctx* ctx, const void* ic_ext, const void* dt0_ext, int64_t nz_ext, int64_t ny, int64_t nx,
+                                 int64_t own_lo, int64_t own_n, int64_t chunk_planes, const of3d_taps* taps, int precision,
+                                 unsigned flags, void* vx, void* vy, void* vz, void* rel);
 
 /* Stream control: the context's stream as a cudaStream_t (for CUDA-event timing by the caller), a caller-supplied
  * stream (of3d_set_stream: every later kernel and copy of the context runs on `cuda_stream`, a cudaStream_t of the

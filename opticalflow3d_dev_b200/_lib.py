@@ -49,6 +49,7 @@ SIGNATURES = {
     'of3d_halo_exchange': (_i, [_vp, C.POINTER(_vp), _i, _sz, _i64, _i64, _i64, _i64, _i64]),
     'of3d_flow3d_slab': (_i, [_vp, C.POINTER(_vp), _i, _i64, _i64, _i64, _i64, _i64, _i64, C.POINTER(Taps), _i, _u,
                               _vp, _vp, _vp, _vp]),
+    'of3d_flow3d_slab_dt': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, C.POINTER(Taps), _i, _u, _vp, _vp, _vp, _vp]),
     'of3d_stream': (_vp, [_vp]),
     'of3d_set_stream': (_i, [_vp, _vp]),
     'of3d_set_async': (_i, [_vp, _i]),
@@ -119,6 +120,7 @@ class Context:
         h = C.c_void_p()
         check(self.lib.of3d_create(self.device, C.byref(h)), 'of3d_create')
         self.handle = h
+        self.is_async = False
 
     def close(self):
         if getattr(self, 'handle', None):
@@ -143,6 +145,7 @@ class Context:
 
     def set_async(self, on):
         check(self.lib.of3d_set_async(self.handle, int(bool(on))), 'of3d_set_async')
+        self.is_async = bool(on)
 
     def set_profile(self, on):
         check(self.lib.of3d_set_profile(self.handle, int(bool(on))), 'of3d_set_profile')

@@ -4,6 +4,7 @@
 // (ni_filters.c NI_Correlate1D, restated in oracle/lk_oracle.py:correlate1d_nearest) with
 // individually rounded multiplies and adds.  Internal header.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "solve.cuh"
 
@@ -57,9 +58,12 @@ __global__ void __launch_bounds__(256) corr_axis_generic(const T* __restrict__ i
 
 // Temporal derivative of the centre frame (calc_flow.py:276-278 / 113-115) and widening of the
 // centre frame to the compute type (calc_flow.py:225 / 67).  frames.p[k] = frame c - r + k.
+// paired (8/16-bit integer frames, antisymmetric taps with a zero centre): dt0 = sum_{l=1..r} w[r+l] (x[r+l] - x[r-l]) with
+// the differences formed exactly in integers and accumulated by FMA in ascending l -- the arithmetic of the fused z march
+// (kernels_tz.cuh), so that the two-stage and the fused pipelines agree bit for bit.
 template <typename Tin, typename T, bool EXACT>
 __global__ void __launch_bounds__(256) temporal_generic(const FramePtrs frames, const Filt<T> f, T* __restrict__ ic,
-                                                        T* __restrict__ dt0, int64_t n) {
+                                                        T* __restrict__ dt0, int64_t n, const int paired) {
     const int r = f.n / 2;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         auto at = [&](int k) -> T { return (T) __ldg(reinterpret_cast<const Tin*>(frames.p[k]) + i); };
@@ -77,7 +81,18 @@ __global__ void __launch_bounds__(256) temporal_generic(const FramePtrs frames, 
             }
         } else {
             acc = T(0);
-            for (int k = 0; k < f.n; ++k) acc = fma(f.w[k], at(k), acc);
+            bool done = false;
+            if constexpr (std::is_integral<Tin>::value && sizeof(Tin) <= 2) {
+                if (paired) {
+                    for (int l = 1; l <= r; ++l) {
+                        const int d = (int)__ldg(reinterpret_cast<const Tin*>(frames.p[r + l]) + i) - (int)__ldg(reinterpret_cast<const Tin*>(frames.p[r - l]) + i);
+                        acc = fma(f.w[r + l], (T)d, acc);
+                    }
+                    done = true;
+                }
+            }
+            if (!done)
+                for (int k = 0; k < f.n; ++k) acc = fma(f.w[k], at(k), acc);
         }
         ic[i] = c;
         dt0[i] = acc;
@@ -106,7 +121,7 @@ __device__ __forceinline__ void store_vec(float* dst, const float (&v)[VEC]) {
 // Requires 16-byte aligned frame pointers; the scalar kernel above handles unaligned frames and the tail.
 template <typename Tin, typename T>
 __global__ void __launch_bounds__(256) temporal_vec(const FramePtrs frames, const Filt<T> f, T* __restrict__ ic,
-                                                    T* __restrict__ dt0, int64_t nvec) {
+                                                    T* __restrict__ dt0, int64_t nvec, const int paired) {
     constexpr int VEC = 16 / sizeof(Tin);
     static_assert(VEC % 2 == 0, "vector width");
     const int r = f.n / 2;
@@ -114,6 +129,26 @@ __global__ void __launch_bounds__(256) temporal_vec(const FramePtrs frames, cons
         T acc[VEC], c[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[j] = T(0);
+        if constexpr (std::is_integral<Tin>::value && sizeof(Tin) <= 2) {
+            if (paired) {                                        // see temporal_generic
+                const uint4 rc = __ldg(reinterpret_cast<const uint4*>(frames.p[r]) + i);
+                const Tin* vc = reinterpret_cast<const Tin*>(&rc);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) c[j] = (T)vc[j];
+                for (int l = 1; l <= r; ++l) {
+                    const uint4 ra = __ldg(reinterpret_cast<const uint4*>(frames.p[r + l]) + i);
+                    const uint4 rb = __ldg(reinterpret_cast<const uint4*>(frames.p[r - l]) + i);
+                    const Tin* va = reinterpret_cast<const Tin*>(&ra);
+                    const Tin* vb = reinterpret_cast<const Tin*>(&rb);
+                    const T w = f.w[r + l];
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) acc[j] = fma(w, (T)((int)va[j] - (int)vb[j]), acc[j]);
+                }
+                store_vec<VEC>(ic + i * VEC, c);
+                store_vec<VEC>(dt0 + i * VEC, acc);
+                continue;
+            }
+        }
         for (int k = 0; k < f.n; ++k) {
             const uint4 raw = __ldg(reinterpret_cast<const uint4*>(frames.p[k]) + i);
             const Tin* v = reinterpret_cast<const Tin*>(&raw);

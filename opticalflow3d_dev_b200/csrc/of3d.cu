@@ -110,6 +110,7 @@ struct GenericPipe {
     of3d_ctx* c;
     Shape s;
     Filt<T> fD, fS, fG, fT, fW;
+    bool tpaired;       // T antisymmetric bit for bit with a zero centre: integer frames use the paired temporal form
 
     void corr(const T* in, T* out, int axis /*0=z,1=y,2=x*/, const Filt<T>& f) {
         const int64_t n = s.n();
@@ -130,6 +131,7 @@ struct GenericPipe {
     void temporal(const FramePtrs& fp, T* ic, T* dt0) {
         StageScope span(c, OF3D_STAGE_TEMPORAL);
         const int64_t n = s.n();
+        const int paired = !EXACT && tpaired;
         if (!EXACT) {
             // 16-byte vector path when every frame (and the outputs) is 16-byte aligned; scalar kernel for the tail
             constexpr int VEC = 16 / sizeof(Tin);
@@ -137,19 +139,19 @@ struct GenericPipe {
             for (int k = 0; k < fT.n; ++k) aligned = aligned && reinterpret_cast<uintptr_t>(fp.p[k]) % 16 == 0;
             const int64_t nvec = aligned ? n / VEC : 0;
             if (nvec > 0) {
-                temporal_vec<Tin, T><<<grid_for(c, nvec), 256, 0, c->stream>>>(fp, fT, ic, dt0, nvec);
+                temporal_vec<Tin, T><<<grid_for(c, nvec), 256, 0, c->stream>>>(fp, fT, ic, dt0, nvec, paired);
                 c->launches++;
                 const int64_t done = nvec * VEC;
                 if (done < n) {
                     FramePtrs tail = fp;
                     for (int k = 0; k < fT.n; ++k) tail.p[k] = reinterpret_cast<const Tin*>(fp.p[k]) + done;
-                    temporal_generic<Tin, T, false><<<grid_for(c, n - done), 256, 0, c->stream>>>(tail, fT, ic + done, dt0 + done, n - done);
+                    temporal_generic<Tin, T, false><<<grid_for(c, n - done), 256, 0, c->stream>>>(tail, fT, ic + done, dt0 + done, n - done, paired);
                     c->launches++;
                 }
                 return;
             }
         }
-        temporal_generic<Tin, T, EXACT><<<grid_for(c, n), 256, 0, c->stream>>>(fp, fT, ic, dt0, n);
+        temporal_generic<Tin, T, EXACT><<<grid_for(c, n), 256, 0, c->stream>>>(fp, fT, ic, dt0, n, paired);
         c->launches++;
     }
 
@@ -229,7 +231,8 @@ static int run_pipe(of3d_ctx* c, const Shape& s, const FramePtrs* fp, int in_dty
                     const T* ic_in, const T* dt0_in, T* ic_out, T* dt0_out, bool spatial, int64_t own_lo, int64_t own_n,
                     T* vx, T* vy, T* vz, T* rel, bool rel_f32) {
     GenericPipe<T, EXACT> g{c, s, make_filt<T>(t->D, t->nD), make_filt<T>(t->S, t->nS), make_filt<T>(t->G, t->nG),
-                            make_filt<T>(t->T, t->nT), make_filt<T>(t->W, t->nW)};
+                            make_filt<T>(t->T, t->nT), make_filt<T>(t->W, t->nW),
+                            taps_symmetric(t->T, t->nT, -1.0) && t->T[t->nT / 2] == 0.0};
     const bool fast = !EXACT && !(flags & OF3D_FLAG_GENERIC) && fast_supported(t);
     // marching kernels with the temporal derivative fused into the z march (kernels_tz.cuh)
     if (fast && spatial && fp && !ic_out && s.ndim == 3 && fused_temporal_ok(t, *fp, in_dtype, s.nx) && !getenv("OF3D_NO_FUSED_T")) {
@@ -937,21 +940,22 @@ OF3D_API int of3d_halo_exchange(of3d_ctx* c, void* const* frames_ext, int n_fram
     return OF3D_OK;
 }
 
-OF3D_API int of3d_flow3d_slab(of3d_ctx* c, const void* const* frames_ext, int in_dtype, int64_t nz_ext, int64_t ny, int64_t nx,
-                              int64_t own_lo, int64_t own_n, int64_t chunk_planes, const of3d_taps* t, int precision, unsigned flags,
-                              void* vx, void* vy, void* vz, void* rel) {
+// The owned range in chunks (interior chunks first: they overlap a halo exchange in flight); frames_ext != nullptr: raw
+// frames, else (ic_ext, dt0_ext) volumes of the compute type
+static int slab_run(of3d_ctx* c, const void* const* frames_ext, const void* ic_ext, const void* dt0_ext, int in_dtype, int64_t nz_ext,
+                    int64_t ny, int64_t nx, int64_t own_lo, int64_t own_n, int64_t chunk_planes, const of3d_taps* t, int precision,
+                    unsigned flags, void* vx, void* vy, void* vz, void* rel) {
     if (!c) { set_error("context is null"); return OF3D_ERR_ARG; }
     if (int rc = check_taps(t)) return rc;
     if (nz_ext < 1 || own_lo < 0 || own_n < 1 || own_lo + own_n > nz_ext || chunk_planes < 0) { set_error("bad z range"); return OF3D_ERR_ARG; }
-    if (!frames_ext || !vx || !vy || !vz || !rel) { set_error("null image or output pointer"); return OF3D_ERR_ARG; }
+    if ((!frames_ext && (!ic_ext || !dt0_ext)) || !vx || !vy || !vz || !rel) { set_error("null image or output pointer"); return OF3D_ERR_ARG; }
     OF3D_CUDA_TRY(cudaSetDevice(c->device));
     const int64_t plane = ny * nx;
     const int64_t H = std::max(std::max(t->nD, t->nG), t->nS) / 2 + t->nW / 2;
-    const size_t ts = precision == OF3D_FP32 ? 4 : 8, ib = dtype_size(in_dtype);
+    const size_t ts = precision == OF3D_FP32 ? 4 : 8, ib = frames_ext ? dtype_size(in_dtype) : ts;
     const size_t rs = (precision == OF3D_FP64 && (flags & OF3D_FLAG_REL_F32)) ? 4 : ts;
     if (!ib) { set_error("unsupported input dtype"); return OF3D_ERR_ARG; }
     const int64_t chunk = chunk_planes ? std::min(chunk_planes, own_n) : own_n;
-    // chunks whose z support lies inside the owned planes run first: they overlap the halo exchange in flight
     std::vector<int64_t> starts, late;
     for (int64_t a = own_lo; a < own_lo + own_n; a += chunk) {
         const int64_t b = std::min(own_lo + own_n, a + chunk);
@@ -963,7 +967,7 @@ OF3D_API int of3d_flow3d_slab(of3d_ctx* c, const void* const* frames_ext, int in
     // one arena size for every chunk (no re-allocation while kernels are queued)
     {
         const int64_t ext_max = std::min(nz_ext, chunk + 2 * H);
-        if (int rc = ws_ensure(c, plan_bytes(3, t->nT, ext_max, chunk, plane, t->nW, in_dtype, precision, OF3D_DEVICE, OF3D_DEVICE, -1, false, true))) return rc;
+        if (int rc = ws_ensure(c, plan_bytes(3, frames_ext ? t->nT : 0, ext_max, chunk, plane, t->nW, in_dtype, precision, OF3D_DEVICE, OF3D_DEVICE, -1, false, true))) return rc;
     }
     const int saved_async = c->async;
     c->async = 1;
@@ -976,21 +980,42 @@ OF3D_API int of3d_flow3d_slab(of3d_ctx* c, const void* const* frames_ext, int in
         }
         const int64_t a = starts[i], b = std::min(own_lo + own_n, a + chunk);
         const int64_t a2 = std::max<int64_t>(0, a - H), b2 = std::min(nz_ext, b + H);
-        const void* frames[kMaxFrames];
-        for (int k = 0; k < t->nT; ++k) {
-            if (!frames_ext[k]) { set_error("null frame pointer"); rc = OF3D_ERR_ARG; break; }
-            frames[k] = static_cast<const char*>(frames_ext[k]) + (size_t)a2 * plane * ib;
-        }
-        if (rc) break;
         const size_t o = (size_t)(a - own_lo) * plane;
-        rc = flow_staged(c, 0, 3, frames, in_dtype, OF3D_DEVICE, b2 - a2, ny, nx, t, precision, flags, nullptr, nullptr,
-                         (char*)vx + o * ts, (char*)vy + o * ts, (char*)vz + o * ts, (char*)rel + o * rs, OF3D_DEVICE, a - a2, b - a);
+        char* ov[4] = {(char*)vx + o * ts, (char*)vy + o * ts, (char*)vz + o * ts, (char*)rel + o * rs};
+        if (frames_ext) {
+            const void* frames[kMaxFrames];
+            for (int k = 0; k < t->nT; ++k) {
+                if (!frames_ext[k]) { set_error("null frame pointer"); rc = OF3D_ERR_ARG; break; }
+                frames[k] = static_cast<const char*>(frames_ext[k]) + (size_t)a2 * plane * ib;
+            }
+            if (rc) break;
+            rc = flow_staged(c, 0, 3, frames, in_dtype, OF3D_DEVICE, b2 - a2, ny, nx, t, precision, flags, nullptr, nullptr,
+                             ov[0], ov[1], ov[2], ov[3], OF3D_DEVICE, a - a2, b - a);
+        } else {
+            rc = flow_staged(c, 2, 3, nullptr, OF3D_U16, OF3D_DEVICE, b2 - a2, ny, nx, t, precision, flags,
+                             (char*)ic_ext + (size_t)a2 * plane * ts, (char*)dt0_ext + (size_t)a2 * plane * ts,
+                             ov[0], ov[1], ov[2], ov[3], OF3D_DEVICE, a - a2, b - a);
+        }
     }
     if (c->halo_pending) { cudaStreamWaitEvent(c->stream, c->ev_halo, 0); c->halo_pending = false; }   // later calls see the halo too
     c->async = saved_async;
     if (rc) { cudaStreamSynchronize(c->stream); return rc; }
     if (!c->async) OF3D_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return OF3D_OK;
+}
+
+OF3D_API int of3d_flow3d_slab(of3d_ctx* c, const void* const* frames_ext, int in_dtype, int64_t nz_ext, int64_t ny, int64_t nx,
+                              int64_t own_lo, int64_t own_n, int64_t chunk_planes, const of3d_taps* t, int precision, unsigned flags,
+                              void* vx, void* vy, void* vz, void* rel) {
+    if (!frames_ext) { set_error("null image or output pointer"); return OF3D_ERR_ARG; }
+    return slab_run(c, frames_ext, nullptr, nullptr, in_dtype, nz_ext, ny, nx, own_lo, own_n, chunk_planes, t, precision, flags, vx, vy, vz, rel);
+}
+
+OF3D_API int of3d_flow3d_slab_dt(of3d_ctx* c, const void* ic_ext, const void* dt0_ext, int64_t nz_ext, int64_t ny, int64_t nx,
+                                 int64_t own_lo, int64_t own_n, int64_t chunk_planes, const of3d_taps* t, int precision, unsigned flags,
+                                 void* vx, void* vy, void* vz, void* rel) {
+    if (!ic_ext || !dt0_ext) { set_error("null ic/dt0 pointer"); return OF3D_ERR_ARG; }
+    return slab_run(c, nullptr, ic_ext, dt0_ext, OF3D_U16, nz_ext, ny, nx, own_lo, own_n, chunk_planes, t, precision, flags, vx, vy, vz, rel);
 }
 
 // ---------------------------------------------------------------------------------------------

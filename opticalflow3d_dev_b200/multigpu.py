@@ -10,9 +10,12 @@ torch.distributed for the plumbing, the library's own NCCL communicator for the 
   R = ceil(3*xyzSig) planes (gradients) plus Rw = ceil(3*wSig) planes (window): H = R + Rw.  Each rank keeps every
   frame of the window in an EXTENDED buffer -- lo <= H halo planes, its own planes, hi <= H halo planes (none at the
   ends of the volume, where the reference's clamp-to-edge applies) -- and
-      1. exchanges the RAW halo planes of every frame with its two neighbours, straight into place: one grouped
-         ncclSend/ncclRecv on the library's exchange stream (of3d_halo_exchange), non-periodic;
-      2. runs of3d_flow3d_slab: every stage works only on the planes the owned range needs (temporal derivative +
+      1. exchanges halo planes with its two neighbours, straight into place: one grouped ncclSend/ncclRecv on the
+         library's exchange stream (of3d_halo_exchange), non-periodic.  exchange='dt' (default): the temporal stage
+         (z-local) runs on the boundary planes first, the halos of (ic, dt0) -- 16 bytes per voxel -- travel while the
+         temporal stage of the interior planes runs; exchange='raw': the raw planes of all kt frames (2 kt bytes per
+         voxel: more bytes for kt > 8, but no temporal pass and no (ic, dt0) volumes);
+      2. runs of3d_flow3d_slab(_dt): every stage works only on the planes the owned range needs (temporal derivative +
          gradient z pass and in-plane passes on own +- Rw, window sums and solve on own), in chunks of `chunk_planes`
          owned planes -- chunks that do not touch a halo run while the exchange is still in flight, and the
          workspace is bounded by the chunk, not by the slab.
@@ -102,7 +105,7 @@ class ZSlab:
     """
 
     def __init__(self, nz_total, ny, nx, dtype, sigmas, *, rank=None, world=None, group=None, precision='fp64',
-                 device=None, chunk_planes=None, rel_dtype='reference', use_nccl=True):
+                 device=None, chunk_planes=None, rel_dtype='reference', use_nccl=True, exchange='dt'):
         import torch
         import torch.distributed as dist
         from . import _lib
@@ -126,7 +129,17 @@ class ZSlab:
         self.kt = self._keep[3].size
         tdev = torch.device('cuda', self.dev)
         tdt = getattr(torch, self.np_dt.name)
-        self.frames = torch.empty((self.kt, self.lo + self.own + self.hi, self.ny, self.nx), dtype=tdt, device=tdev)
+        if exchange not in ('dt', 'raw'):
+            raise ValueError("exchange must be 'dt' or 'raw'")
+        self.mode = exchange
+        self.odt = torch.float64 if precision == 'fp64' else torch.float32
+        next_ = self.lo + self.own + self.hi
+        if self.mode == 'raw':
+            self.frames = torch.empty((self.kt, next_, self.ny, self.nx), dtype=tdt, device=tdev)
+        else:
+            self.frames = torch.empty((self.kt, self.own, self.ny, self.nx), dtype=tdt, device=tdev)
+            self.ic = torch.empty((next_, self.ny, self.nx), dtype=self.odt, device=tdev)
+            self.dt0 = torch.empty((next_, self.ny, self.nx), dtype=self.odt, device=tdev)
         self.rel_f32 = precision == 'fp64' and rel_dtype == 'reference'
         # chunk of owned planes per pass: bounds the workspace (about 13 compute-type volumes of chunk + 2 Rw planes)
         self.chunk = int(chunk_planes) if chunk_planes is not None else 0
@@ -134,7 +147,23 @@ class ZSlab:
         self.use_nccl = use_nccl and self.world > 1
 
     def own_frames(self):
-        return self.frames[:, self.lo:self.lo + self.own]
+        """(kt, own, ny, nx) view to fill with this rank's planes of the kt frames around the centre"""
+        return self.frames[:, self.lo:self.lo + self.own] if self.mode == 'raw' else self.frames
+
+    def _temporal(self, p0, p1):
+        """temporal stage of the owned planes [p0, p1) into the extended (ic, dt0) volumes (asynchronous)"""
+        from . import _lib
+        if p1 <= p0:
+            return
+        plane = self.ny * self.nx
+        fb = self.own * plane * self.frames.element_size()
+        off = p0 * plane * self.frames.element_size()
+        ptrs = (C.c_void_p * self.kt)(*[self.frames.data_ptr() + k * fb + off for k in range(self.kt)])
+        es = self.ic.element_size()
+        o = (self.lo + p0) * plane * es
+        rc = self.ctx.lib.of3d_temporal(self.ctx.handle, 3, ptrs, self.code, _lib.DEVICE, p1 - p0, self.ny, self.nx, C.byref(self.taps),
+                                        _lib.FP64 if self.precision == 'fp64' else _lib.FP32, 0, self.ic.data_ptr() + o, self.dt0.data_ptr() + o)
+        _lib.check(rc, 'of3d_temporal')
 
     def _init_comm(self):
         """rank 0's NCCL id reaches every rank through torch.distributed; the communicator lives in the library"""
@@ -159,18 +188,41 @@ class ZSlab:
     def exchange(self):
         """Start the halo exchange of every frame (returns at once; flow() waits for it on the device where needed).
         The caller's writes to own_frames() on torch's current stream are ordered before it."""
-        if self.world == 1:
-            return
         from . import _lib
         torch = self.torch
         plans = self.plan['_all']
         send_dn = plans[self.rank - 1]['hi'] if self.rank > 0 else 0
         send_up = plans[self.rank + 1]['lo'] if self.rank + 1 < self.world else 0
+        torch.cuda.current_stream(self.dev).synchronize()
+        if self.mode == 'dt':
+            # boundary planes first, then the exchange of (ic, dt0) starts while the interior planes are computed
+            was_async = self.ctx.is_async
+            self.ctx.set_async(True)
+            try:
+                if self.world == 1 or send_dn + send_up >= self.own:
+                    self._temporal(0, self.own)
+                    split = None
+                else:
+                    self._temporal(0, send_dn)
+                    self._temporal(self.own - send_up, self.own)
+                    split = (send_dn, self.own - send_up)
+                if self.world > 1:
+                    self._init_comm()
+                    ptrs = (C.c_void_p * 2)(self.ic.data_ptr(), self.dt0.data_ptr())
+                    rc = self.ctx.lib.of3d_halo_exchange(self.ctx.handle, ptrs, 2, self.ny * self.nx * self.ic.element_size(),
+                                                         self.lo, self.own, self.hi, send_dn, send_up)
+                    _lib.check(rc, 'of3d_halo_exchange')
+                if split:
+                    self._temporal(*split)
+            finally:
+                self.ctx.set_async(was_async)
+            return
+        if self.world == 1:
+            return
         if not self.use_nccl:
             exchange_frames_torch(self.frames, self.plan, self.rank, self.world, self.group)
             return
         self._init_comm()
-        torch.cuda.current_stream(self.dev).synchronize()
         fb = self.frames[0].numel() * self.frames.element_size()
         ptrs = (C.c_void_p * self.kt)(*[self.frames.data_ptr() + k * fb for k in range(self.kt)])
         rc = self.ctx.lib.of3d_halo_exchange(self.ctx.handle, ptrs, self.kt, self.ny * self.nx * self.frames.element_size(),
@@ -187,10 +239,17 @@ class ZSlab:
         if out is None:
             out = [torch.empty(sp, dtype=odt, device=tdev) for _ in range(3)]
             out.append(torch.empty(sp, dtype=torch.float32 if self.rel_f32 else odt, device=tdev))
-        fb = self.frames[0].numel() * self.frames.element_size()
-        ptrs = (C.c_void_p * self.kt)(*[self.frames.data_ptr() + k * fb for k in range(self.kt)])
         torch.cuda.current_stream(self.dev).synchronize()
         flags = _lib.FLAG_REL_F32 if self.rel_f32 else 0
+        if self.mode == 'dt':
+            rc = self.ctx.lib.of3d_flow3d_slab_dt(self.ctx.handle, self.ic.data_ptr(), self.dt0.data_ptr(), self.lo + self.own + self.hi,
+                                                  self.ny, self.nx, self.lo, self.own, self.chunk, C.byref(self.taps),
+                                                  _lib.FP64 if self.precision == 'fp64' else _lib.FP32, flags,
+                                                  *[o.data_ptr() for o in out])
+            _lib.check(rc, 'of3d_flow3d_slab_dt')
+            return tuple(out)
+        fb = self.frames[0].numel() * self.frames.element_size()
+        ptrs = (C.c_void_p * self.kt)(*[self.frames.data_ptr() + k * fb for k in range(self.kt)])
         rc = self.ctx.lib.of3d_flow3d_slab(self.ctx.handle, ptrs, self.code, self.lo + self.own + self.hi, self.ny, self.nx,
                                            self.lo, self.own, self.chunk, C.byref(self.taps),
                                            _lib.FP64 if self.precision == 'fp64' else _lib.FP32, flags,
@@ -205,7 +264,7 @@ class ZSlab:
 
 
 def calc_flow3D_zslab(frames_local, xyzSig=3, tSig=1, wSig=4, *, nz_total, rank=None, world=None, group=None, precision='fp64',
-                      chunk_planes=None, rel_dtype='float64', exchange_fn=None, flow_fn=None):
+                      chunk_planes=None, rel_dtype='float64', exchange='dt', exchange_fn=None, flow_fn=None):
     """
     calc_flow3D on a volume sharded by z-slab.  `frames_local` is this rank's (Nt, nz_own, Ny, Nx) block (CUDA tensor;
     any strides), the blocks being the contiguous split of `nz_total` planes given by `plan_slabs`.  Nt follows the
@@ -242,7 +301,8 @@ def calc_flow3D_zslab(frames_local, xyzSig=3, tSig=1, wSig=4, *, nz_total, rank=
         (exchange_fn or exchange_frames_torch)(ext, plan, rank, world, group)
         return flow_fn(ext, lo, own)
     zs = ZSlab(nz_total, ny, nx, _np_dtype(frames_local), (xyzSig, tSig, wSig), rank=rank, world=world, group=group,
-               precision=precision, device=frames_local.device.index, chunk_planes=chunk_planes, rel_dtype=rel_dtype)
+               precision=precision, device=frames_local.device.index, chunk_planes=chunk_planes, rel_dtype=rel_dtype,
+               exchange=exchange)
     try:
         zs.own_frames().copy_(frames_local[c0:c0 + kt])   # strided views are fine: copy_ handles them
         zs.exchange()

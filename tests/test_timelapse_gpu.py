@@ -99,7 +99,7 @@ def test_two_stage_abi_equals_single_call():
         multigpu._cuda_temporal(torch.cat([fr, fr[:1]]), (3, 1, 4), 'fp64', 0)
 
 
-def _nccl_worker(rank, world, port, shape, sig, seed, chunk, q):
+def _nccl_worker(rank, world, port, shape, sig, seed, chunk, mode, q):
     import torch
     import torch.distributed as dist
     from opticalflow3d_dev_b200 import multigpu
@@ -110,17 +110,18 @@ def _nccl_worker(rank, world, port, shape, sig, seed, chunk, q):
         img = make_stack(shape, seed=seed, dtype=np.uint16)
         z0, z1 = multigpu.shard_timepoints(shape[1], world)[rank]
         local = torch.from_numpy(img).cuda()[:, z0:z1]                 # strided view: the engine copies it into place
-        out = multigpu.calc_flow3D_zslab(local, *sig, nz_total=shape[1], chunk_planes=chunk)
+        out = multigpu.calc_flow3D_zslab(local, *sig, nz_total=shape[1], chunk_planes=chunk, exchange=mode)
         q.put((rank, [o.cpu().numpy() for o in out]))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('chunk', [None, 8])
-def test_zslab_nccl_two_gpus(chunk):
-    """z-slab sharding over two B200s: in-library NCCL halo exchange of the raw frames + of3d_flow3d_slab, bit-identical
-    to the single-GPU result (whole slab, and in chunks of 8 planes with the interior chunks ahead of the exchange)."""
+@pytest.mark.parametrize('chunk,mode', [(None, 'dt'), (8, 'dt'), (None, 'raw'), (8, 'raw')])
+def test_zslab_nccl_two_gpus(chunk, mode):
+    """z-slab sharding over two B200s: in-library NCCL halo exchange -- of (ic, dt0) after a boundary-first temporal stage,
+    or of the raw frames -- + of3d_flow3d_slab(_dt), bit-identical to the single-GPU result (whole slab, and in chunks
+    of 8 planes with the interior chunks ahead of the exchange)."""
     import torch
     import torch.multiprocessing as mp
     from opticalflow3d_dev_b200.calc_flow import calc_flow3D
@@ -130,7 +131,7 @@ def test_zslab_nccl_two_gpus(chunk):
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, shape, sig, seed, chunk, q)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, shape, sig, seed, chunk, mode, q)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=300) for _ in range(2))
@@ -177,6 +178,22 @@ def test_flow3d_slab_ranges_and_chunks_are_bit_identical(shape, sig, precision, 
         _lib.check(rc, 'of3d_flow3d_slab')
         for o, r in zip(outs, ref):
             assert torch.equal(o, r[z0:z1]), (z0, z1, chunk)
+        # the same range from extended (ic, dt0) volumes (of3d_temporal + of3d_flow3d_slab_dt): integer frames use the
+        # fused march's temporal arithmetic, so the two-stage path is bit-identical as well (float frames: to rounding)
+        ic = torch.empty((e1 - e0, ny, nx), dtype=odt, device='cuda')
+        dt0 = torch.empty_like(ic)
+        outs2 = [torch.empty_like(o) for o in outs]
+        torch.cuda.synchronize()
+        _lib.check(ctx.lib.of3d_temporal(ctx.handle, 3, ptrs, _lib.DTYPE_CODES[np.dtype(dtype)], _lib.DEVICE, e1 - e0, ny, nx, C.byref(taps),
+                                         _lib.FP64 if precision == 'fp64' else _lib.FP32, 0, ic.data_ptr(), dt0.data_ptr()), 'of3d_temporal')
+        rc = ctx.lib.of3d_flow3d_slab_dt(ctx.handle, ic.data_ptr(), dt0.data_ptr(), e1 - e0, ny, nx, z0 - e0, z1 - z0, chunk,
+                                         C.byref(taps), _lib.FP64 if precision == 'fp64' else _lib.FP32, 0, *[o.data_ptr() for o in outs2])
+        _lib.check(rc, 'of3d_flow3d_slab_dt')
+        for o, r in zip(outs2, outs):
+            if np.dtype(dtype).kind == 'u':
+                assert torch.equal(o, r), (z0, z1, chunk, 'dt')
+            else:
+                assert float((o - r).abs().max()) <= 1e-9 * max(float(r.abs().max()), 1e-30)
     # bad ranges are rejected
     assert ctx.lib.of3d_flow3d_slab(ctx.handle, ptrs, _lib.U16, 10, ny, nx, 5, 6, 0, C.byref(taps), _lib.FP64, 0,
                                     *[o.data_ptr() for o in outs]) == -1
