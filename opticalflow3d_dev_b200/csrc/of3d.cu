@@ -639,7 +639,11 @@ static int window_flow_pipelined(of3d_ctx* c, int in_dtype, int64_t nz, int64_t 
         c->pipe_cap = need;
     }
     // one arena size for every stage call of the pipeline (no re-allocation in flight)
-    if (int rc = ws_ensure(c, plan_bytes(3, t->nT, ext_max, std::min(slab, nz), plane, t->nW, in_dtype, precision, OF3D_DEVICE, OF3D_DEVICE, -1, false, true))) return rc;
+    {
+        const bool fast = !(flags & (OF3D_FLAG_EXACT | OF3D_FLAG_GENERIC)) && fast_supported(t);
+        if (int rc = ws_ensure(c, plan_bytes(3, t->nT, ext_max, std::min(slab, nz), plane, t->nW, in_dtype, precision, OF3D_DEVICE, OF3D_DEVICE,
+                                             fast ? 1 : 0, false, (flags & OF3D_FLAG_REL_F32) != 0))) return rc;
+    }
     char* ext[2][4];
     for (int q = 0; q < 2; ++q) for (int i = 0; i < 4; ++i) ext[q][i] = c->pipe + (size_t)(q * 4 + i) * out_b;
     const size_t slot = align_up(c->win_frame);
@@ -967,7 +971,9 @@ static int slab_run(of3d_ctx* c, const void* const* frames_ext, const void* ic_e
     // one arena size for every chunk (no re-allocation while kernels are queued)
     {
         const int64_t ext_max = std::min(nz_ext, chunk + 2 * H);
-        if (int rc = ws_ensure(c, plan_bytes(3, frames_ext ? t->nT : 0, ext_max, chunk, plane, t->nW, in_dtype, precision, OF3D_DEVICE, OF3D_DEVICE, -1, false, true))) return rc;
+        const bool fast = !(flags & (OF3D_FLAG_EXACT | OF3D_FLAG_GENERIC)) && fast_supported(t);
+        if (int rc = ws_ensure(c, plan_bytes(3, frames_ext ? t->nT : 0, ext_max, chunk, plane, t->nW, in_dtype, precision, OF3D_DEVICE, OF3D_DEVICE,
+                                             fast ? 1 : 0, false, (flags & OF3D_FLAG_REL_F32) != 0))) return rc;
     }
     const int saved_async = c->async;
     c->async = 1;

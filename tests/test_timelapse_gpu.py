@@ -83,13 +83,16 @@ def test_two_stage_abi_equals_single_call():
     from opticalflow3d_dev_b200.calc_flow import calc_flow3D
     img = make_stack((7, 12, 40, 36), seed=33, dtype=np.uint16)
     ref = calc_flow3D(img, 3, 1, 4, rel_dtype='float64')
-    fr = torch.from_numpy(img.astype(np.int32)).cuda()
+    fr = torch.from_numpy(img).cuda()                           # uint16: the temporal kernels use the fused march's arithmetic
     ic, dt0 = multigpu._cuda_temporal(fr, (3, 1, 4), 'fp64', 0)
     assert np.array_equal(ic.cpu().numpy(), img[3].astype(np.float64))
     outs = multigpu._cuda_spatial(ic, dt0, (3, 1, 4), 'fp64', 0)
     assert all(np.array_equal(o.cpu().numpy(), r) for o, r in zip(outs, ref))
+    # wider integer frames take the plain tap-by-tap temporal sum: equal to rounding
+    ic3, dt3 = multigpu._cuda_temporal(torch.from_numpy(img.astype(np.int32)).cuda(), (3, 1, 4), 'fp64', 0)
+    assert torch.equal(ic3, ic) and float((dt3 - dt0).abs().max()) <= 1e-12 * float(dt0.abs().max())
     # a sliced (non-contiguous) z range of a longer stack gives the same planes; short / even stacks exit like the reference
-    pad = np.full((9, 17, 40, 36), 7, np.int32)
+    pad = np.full((9, 17, 40, 36), 7, np.uint16)
     pad[1:8, 2:14] = img
     ic2, dt2 = multigpu._cuda_temporal(torch.from_numpy(pad).cuda()[:, 2:14], (3, 1, 4), 'fp64', 0)
     assert torch.equal(ic2, ic) and torch.equal(dt2, dt0)
