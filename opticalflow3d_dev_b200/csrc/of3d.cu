@@ -344,8 +344,11 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
             if (in_mem == OF3D_DEVICE) for (int k = 0; k < t->nT; ++k) probe.p[k] = frames[k];
             fused = fused_temporal_ok(t, probe, in_dtype, nx);
         }
-        if (int rc = ws_ensure(c, plan_bytes(ndim, stage == 2 ? 0 : t->nT, nz, own_n, ny * nx, t->nW, in_dtype, precision,
-                                             stage == 2 ? OF3D_DEVICE : in_mem, stage == 1 ? OF3D_DEVICE : out_mem, fast ? 1 : 0, fused, rel_f32))) return rc;
+        // (the temporal stage alone writes straight into the caller's ic / dt0: it only needs the staging of host frames)
+        const size_t need = stage == 1 ? (in_mem == OF3D_HOST ? (size_t)t->nT * align_up((size_t)n * dtype_size(in_dtype)) + 8192 : 8192)
+                                       : plan_bytes(ndim, stage == 2 ? 0 : t->nT, nz, own_n, ny * nx, t->nW, in_dtype, precision,
+                                                    stage == 2 ? OF3D_DEVICE : in_mem, out_mem, fast ? 1 : 0, fused || stage == 2, rel_f32);
+        if (int rc = ws_ensure(c, need)) return rc;
     }
     c->ws_off = 0;
 
