@@ -42,6 +42,8 @@ WORKLOADS = {
     # one 19-frame window of a 2048x2048x512 volume: too large for one GPU, sharded by z-slab with an NCCL halo
     # exchange (needs --gpus >= 4 in fp64, >= 2 in fp32)
     'cfg5': dict(shape=(19, 512, 2048, 2048), sig=(3, 3, 8), zslab=True),
+    # (debug) the kernels of cfg5 on one GPU: a 112-plane slab -- 64 owned planes + 2 x 24 window planes -- of the cfg5 volume
+    'cfg5slab': dict(shape=(21, 112, 2048, 2048), sig=(3, 3, 8)),
 }
 METRIC = 'output voxels/s (vx,vy,vz,rel) 1024x1024x128 stack'
 UNIT = 'voxels/s'
@@ -51,6 +53,7 @@ METRICS = {
     'cfg3': 'output voxels/s (vx,vy,vz,rel) 512x512x64 stack, 31 timepoints',
     'cfg4': METRIC,
     'cfg5': 'output voxels/s (vx,vy,vz,rel) 2048x2048x512 volume, z-slab sharded',
+    'cfg5slab': 'output voxels/s (vx,vy,vz,rel) 2048x2048x112 slab of the cfg5 volume (kernel study)',
 }
 REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
 
@@ -357,6 +360,7 @@ def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, ste
                          rel_dtype='float64', exchange=mode)
     tmp = fill(zs_, zs_.z0, nz_total)
     outs = None
+    chunk_used = zs_.chunk
 
     def step():
         zs_.exchange()
@@ -390,6 +394,8 @@ def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, ste
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     ctx.set_async(True)
     l0 = ctx.launch_count()
+    ctx.stage_times()
+    ctx.set_profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
@@ -398,6 +404,8 @@ def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, ste
     ctx.set_async(False)
     barrier()
     ms = e0.elapsed_time(e1)
+    stages = ctx.stage_times()
+    ctx.set_profile(False)
     stat = torch.tensor([ms, float(ctx.launch_count() - l0), 0.0 if halo_ok else 1.0], dtype=torch.float64, device=dev)
     tmax = stat.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -421,7 +429,7 @@ def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, ste
         'n_gpus': world, 'steps': steps, 'ms_per_step': float(tmax[0].item()) / steps, 'scaling': 'weak' if nz_total != 512 else 'strong',
         'dtype': 'f64' if precision == 'fp64' else 'f32',
         'config': {'shape': [kt, nz_total, ny, nx], 'sigmas': list(sig), 'input_dtype': 'uint16', 'planes_per_rank': nz_total // world,
-                   'chunk_planes': chunk_planes,
+                   'chunk_planes': chunk_used,
                    'exchange': mode,
                    'sharding': ('z-slab; temporal stage on the boundary planes, then %d halo planes of (ic, dt0) exchanged with each '
                                 'neighbour by the library (grouped ncclSend/ncclRecv, in place) while the interior temporal stage '
@@ -430,6 +438,7 @@ def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, ste
                                 'library (grouped ncclSend/ncclRecv, in place); interior chunks overlap the exchange' % (H, kt)),
                    'halo_bytes_sent_per_interior_rank_per_step': int(2 * H * ny * nx * (2 * (8 if precision == 'fp64' else 4) if mode == 'dt' else kt * es))},
         'parity_small_volume_bit_identical': parity, 'halo_planes_verified': bool(stat[2].item() == 0.0),
+        'stages_ms_per_step_rank0': {k: round(v[0] / steps, 3) for k, v in stages.items()},
         'free_hbm_bytes_rank0_after': int(mem[0]),
         'roofline': {'bound': 'hbm', 'achieved': value * bpv / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
                      'frac': value * bpv / 1e9 / world / peak, 'peak_source': peak_src, 'alg_bytes_per_voxel': bpv,
@@ -500,7 +509,7 @@ def device_measure(ctx, local_rank, rank, world, workload, precision, timepoints
     frames = torch.empty((max(nloc, 1), nz, ny, nx), dtype=torch.int16, device=dev)
     torch.cuda.synchronize()
     if mine:
-        _lib.check(lib.of3d_synth_blobs(ctx.handle, frames.data_ptr(), nloc, nz, ny, nx, mine[0] - rt, 0, 1000 + int(workload[3:])), 'synth')
+        _lib.check(lib.of3d_synth_blobs(ctx.handle, frames.data_ptr(), nloc, nz, ny, nx, mine[0] - rt, 0, 1000 + int(workload[3:4])), 'synth')
     outs = [torch.empty((nz, ny, nx), dtype=odt, device=dev) for _ in range(ndim + 1)]
     optr = [C.c_void_p(o.data_ptr()) for o in outs]
     if ndim == 2:
@@ -694,13 +703,32 @@ def gpu_arm(args, rank, world, local_rank):
             _lib.pinned_pool_trim()
         if not n_e2e:
             h2d = d2h = 0
+        # the box's ceiling for this number: every rank copies a pinned 1 GiB buffer device -> host for ~1 s, all ranks
+        # at once (plain cudaMemcpyAsync, no engine); e2e moves d2h_bytes_per_voxel bytes per voxel over the same links
+        ceil_gbs = 0.0
+        if n_e2e or world > 1:
+            cb_d = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+            cb_h = torch.from_numpy(_lib.pinned_empty((1 << 30,), np.uint8))
+            cb_h.copy_(cb_d, non_blocking=True); torch.cuda.synchronize()
+            barrier()
+            tcp = time.perf_counter(); reps = 0
+            while time.perf_counter() - tcp < 1.0:
+                cb_h.copy_(cb_d, non_blocking=True); torch.cuda.synchronize(); reps += 1
+            ceil_gbs = reps * (1 << 30) / (time.perf_counter() - tcp) / 1e9
+            del cb_d, cb_h
+            _lib.pinned_pool_trim()
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        nn = torch.tensor([float(n_e2e), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+        nn = torch.tensor([float(n_e2e), float(h2d), float(d2h), ceil_gbs], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(nn, op=dist.ReduceOp.SUM)
         e2e = {'value': float(nn[0].item()) * vol / float(tt.item()), 'unit': UNIT,
                'h2d_bytes_per_step': int(nn[1].item()), 'd2h_bytes_per_step': int(nn[2].item()),
                'timepoints': int(nn[0].item()),
+               'd2h_ceiling_gbs': float(nn[3].item()),
+               'd2h_gbs': (float(nn[2].item()) / float(tt.item()) / 1e9) if float(tt.item()) > 0 else None,
+               'frac_of_d2h_ceiling': (float(nn[2].item()) / float(tt.item()) / 1e9 / float(nn[3].item())) if float(nn[3].item()) > 0 else None,
+               'ceiling_note': 'aggregate pinned device->host copy rate of all ranks copying at once, measured here (the GPUs of '
+                               'this box share PCIe uplinks: tools/pcie_bw.py --gpus N, profiles/r02_pcie_concurrent_4gpu.jsonl)',
                'api': 'timelapse.FlowStream.push(host frame) -> host (vx,vy,vz,rel), pinned; the engine under process_flow',
                'numa_bound_cpus': (len(cpus) if cpus else None),
                'calc_flow_call_value': call_rate,
@@ -787,7 +815,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-voxels', type=int, default=400_000, help='voxels per core per CPU step')
     ap.add_argument('--cpu-cores', type=int, default=None, help='processes of the CPU arm (default 16, or all cores if fewer)')
-    ap.add_argument('--chunk-planes', type=int, default=64, help='z-slab runs: owned planes per pass of the slab pipeline')
+    ap.add_argument('--chunk-planes', type=int, default=None, help='z-slab runs: owned planes per pass of the slab pipeline (default: as large as the free HBM allows)')
     ap.add_argument('--zslab-exchange', default='dt', choices=['dt', 'raw'], help="halo exchange of (ic, dt0) or of the raw frames")
     ap.add_argument('--no-zslab', action='store_true', help='multi-GPU runs: skip the z-slab sub-record')
     ap.add_argument('--no-configs', action='store_true', help='single-GPU runs: skip the quick lines of the other BASELINE configs')

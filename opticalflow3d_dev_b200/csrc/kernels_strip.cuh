@@ -427,6 +427,16 @@ __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const 
 #pragma unroll
     for (int i = 0; i < P; ++i) acc[i] = T(0);
 
+    auto solve_batch = [&](int bb) {
+#pragma unroll 1
+        for (int ui = 0; ui < 4; ++ui) {
+            const int unit = solve_unit<NCH, NHALF>(warp, ui);
+            if (unit < 0) break;
+            solve_unit_voxels<T, NCH, TX, R>(park, PARKROW, bb, unit, lane, cs0, nout, g.n_c, (int64_t)o * g.stride_o, g.stride_m, m0,
+                                             a.vx, a.vy, a.vz, a.rel, a.rel_f32);
+        }
+    };
+
     st.issue(0);
     int b = 0;
 #pragma unroll 1
@@ -449,14 +459,7 @@ __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const 
                 }
             }
             __syncthreads();                                                  // one batch of outputs parked by all channels
-            // ---------------- solve the RB x TX outputs of batch b
-#pragma unroll 1
-            for (int ui = 0; ui < 4; ++ui) {
-                const int unit = solve_unit<NCH, NHALF>(warp, ui);
-                if (unit < 0) break;
-                solve_unit_voxels<T, NCH, TX, R>(park, PARKROW, b, unit, lane, cs0, nout, g.n_c, (int64_t)o * g.stride_o, g.stride_m, m0,
-                                                 a.vx, a.vy, a.vz, a.rel, a.rel_f32);
-            }
+            solve_batch(b);                                                   // the RB x TX outputs of batch b
         }
     }
     cp_async_wait<0>();

@@ -68,6 +68,22 @@ def _np_dtype(t):
     return np.dtype(str(t.dtype).replace('torch.', ''))
 
 
+def slab_workspace_bytes(chunk, plane, ts, rw, halo):
+    """device workspace of one chunk of `chunk` owned planes (plan_bytes in csrc/of3d.cu, marching pipeline from (ic, dt0)
+    or raw frames): the three z-pass volumes aliased with the nine z-windowed products, four gradient volumes on
+    chunk + 2 Rw planes, and (ic, dt0) of chunk + 2 H planes when the temporal stage is not fused"""
+    ng = chunk + 2 * rw
+    return (max(3 * ng, 9 * chunk) + 4 * ng + 2 * (chunk + 2 * halo)) * plane * ts
+
+
+def auto_chunk(own, plane, ts, rw, halo, budget):
+    """largest chunk (<= own) whose workspace fits `budget` bytes, at least 8 planes"""
+    c = own
+    while c > 8 and slab_workspace_bytes(c, plane, ts, rw, halo) > budget:
+        c = max(8, (c + 1) // 2)
+    return int(c)
+
+
 def exchange_frames_torch(ext, plan, rank, world, group=None):
     """Halo exchange of the extended frames tensor (kt, lo + own + hi, ...) with torch.distributed P2P (gloo on CPU
     ranks; the CUDA path uses the library's NCCL exchange).  Receives land in place: slices along z of every frame."""
@@ -141,8 +157,15 @@ class ZSlab:
             self.ic = torch.empty((next_, self.ny, self.nx), dtype=self.odt, device=tdev)
             self.dt0 = torch.empty((next_, self.ny, self.nx), dtype=self.odt, device=tdev)
         self.rel_f32 = precision == 'fp64' and rel_dtype == 'reference'
-        # chunk of owned planes per pass: bounds the workspace (about 13 compute-type volumes of chunk + 2 Rw planes)
-        self.chunk = int(chunk_planes) if chunk_planes is not None else 0
+        # chunk of owned planes per pass of the slab pipeline: bounds the workspace.  None: the largest chunk whose workspace
+        # fits 70 % of the HBM that is free now (fewer chunks = less redundant gradient work on the 2 Rw planes around each)
+        if chunk_planes is None:
+            free = torch.cuda.mem_get_info(self.dev)[0]
+            ts = 8 if precision == 'fp64' else 4
+            outs = 4 * self.own * self.ny * self.nx * ts                       # flow() allocates the results afterwards
+            self.chunk = auto_chunk(self.own, self.ny * self.nx, ts, math.ceil(3 * self.sig[2]), self.H, 0.7 * free - outs)
+        else:
+            self.chunk = int(chunk_planes)
         self._comm_ready = False
         self.use_nccl = use_nccl and self.world > 1
 

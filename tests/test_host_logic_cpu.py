@@ -133,3 +133,13 @@ def test_boundary_dtype_mapping():
         assert _device_dtype(dt) == np.float64
     with pytest.raises(TypeError):
         _device_dtype(np.complex64)
+
+
+def test_zslab_auto_chunk():
+    """the slab pipeline's chunk is the largest one whose workspace fits the budget (multigpu.auto_chunk)"""
+    from opticalflow3d_dev_b200 import multigpu
+    plane, ts, rw, h = 2048 * 2048, 8, 24, 33
+    assert multigpu.auto_chunk(64, plane, ts, rw, h, 200e9) == 64
+    c = multigpu.auto_chunk(256, plane, ts, rw, h, 60e9)
+    assert 8 <= c < 256 and multigpu.slab_workspace_bytes(c, plane, ts, rw, h) <= 60e9 < multigpu.slab_workspace_bytes(2 * c, plane, ts, rw, h)
+    assert multigpu.auto_chunk(256, plane, ts, rw, h, 1e9) == 8
