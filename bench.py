@@ -104,9 +104,9 @@ def fma_peak(precision):
 
 def measured_traffic(workload, precision):
     """DRAM bytes per output voxel of the whole per-timepoint pipeline, from the committed ncu launch lists
-    (profiles/r01_traffic.json: sum of dram__bytes_read.sum + dram__bytes_write.sum over the launches of one timepoint)."""
+    (profiles/r02_traffic.json: sum of dram__bytes_read.sum + dram__bytes_write.sum over the launches of one timepoint)."""
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as fh:
+        with open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')) as fh:
             return json.load(fh).get('%s_%s' % (workload, precision))
     except Exception:
         return None
