@@ -109,6 +109,7 @@ def test_golden_fp32_mode(name):
 @pytest.mark.parametrize('shape,sig,dtype', [
     ((7, 24, 70, 100), (3, 1, 4), np.uint16),       # BASELINE cfg4 parameters, cropped
     ((7, 32, 64, 64), (1, 1, 4), np.uint16),        # BASELINE cfg1 parameters, cropped
+    ((7, 32, 128, 128), (1, 1, 4), np.uint16),      # BASELINE cfg1 at its FULL size (the oracle needs ~5 s)
     ((13, 20, 50, 60), (3, 2, 6), np.uint16),       # cfg3 parameters
     ((19, 6, 20, 130), (3, 3, 8), np.float32),      # cfg5 parameters; window wider than z and y
     ((7, 3, 5, 4), (1, 1, 4), np.uint8),            # volume smaller than every filter
@@ -288,7 +289,15 @@ def test_full_size_fast_path_matches_generic_kernels(shape, sig, ndim):
     lam = float(gen[-1].abs().max())
     assert float((fast[-1] - gen[-1]).abs().max()) <= 1e-10 * lam
     assert float(fast[-1].min()) > -1e-9 * lam          # smallest eigenvalue of a PSD window tensor
-    del fast, gen, win
+    # fp32 mode at full size against the fp64 generic result, at the fp32 tolerance of the goldens:
+    # |dv| <= 1e-4 max|v| where the reliability exceeds its median; reliability 1e-4 lambda_max
+    f32 = fn(win, *sig, precision='fp32')
+    mask = gen[-1] > gen[-1].float().median().double()
+    for f, g in zip(f32[:-1], gen[:-1]):
+        assert f.dtype == torch.float32 and torch.isfinite(f).all()
+        assert float((f.double() - g)[mask].abs().max()) <= 1e-4 * vmax
+    assert float((f32[-1].double() - gen[-1]).abs().max()) <= 1e-4 * lam
+    del fast, gen, win, f32, mask
     torch.cuda.empty_cache()
 
 
