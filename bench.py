@@ -745,8 +745,11 @@ def gpu_arm(args, rank, world, local_rank):
     zrec = None
     if world > 1 and not args.no_zslab and args.workload == 'cfg4':
         w5 = WORKLOADS['cfg5']
-        zrec = zslab_measure(rank, world, local_rank, w5['sig'], 64 * world, w5['shape'][2], w5['shape'][3], args.precision, 2, 1,
-                             args.chunk_planes, mode=args.zslab_exchange)
+        try:
+            zrec = zslab_measure(rank, world, local_rank, w5['sig'], 64 * world, w5['shape'][2], w5['shape'][3], args.precision, 2, 1,
+                                 args.chunk_planes, mode=args.zslab_exchange)
+        except Exception as exc:                                  # the headline line must survive a failing sub-record
+            zrec = {'error': '%s: %s' % (type(exc).__name__, exc)}
 
     # ---- the other BASELINE configs, device-timed on a few timepoints each (single-GPU runs)
     configs = None

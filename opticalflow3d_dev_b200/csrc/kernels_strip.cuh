@@ -387,6 +387,22 @@ __device__ __forceinline__ void solve_unit_voxels(const T* park, int parkrow, in
     }
 }
 
+// y march of one batch (rows BI * RB .. BI * RB + RB - 1 of the unroll period): scatter the gathered rows into the ring
+// and park the completed rows (output j = s - 2R lives in park row j mod RB)
+template <typename T, int K, int P, int BI, typename Stage>
+__device__ __forceinline__ void strip_march_batch(T (&acc)[P], const Taps<T, K>& f, const Stage& st, T* pk, int parkrow) {
+    constexpr int RB = kStripRB, R = K / 2;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+        const T res = ring_push<T, K, P, 1>(acc, f, st.gathered(r), BI * RB + r);
+        constexpr int kBias = (2 * R + RB - 1) / RB * RB;
+        pk[((r + kBias - 2 * R) % RB) * parkrow] = res;
+    }
+}
+
+// COMPACT (fp64 windows longer than 25 taps): one copy of the gather and of the solve in the instruction stream, the
+// batch of the period selected by a uniform switch -- the fully unrolled period of the 49-tap kernel is 155 KB of SASS
+// (7 copies of a 392-DFMA gather) and stalls 1.6 cycles per issue on instruction fetch.
 template <typename T, int K, int P, int NCH, int NHALF, bool PROD>
 __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const StripArgs<T, K> a) {
     constexpr int RB = kStripRB, R = K / 2, TX = 32 * NHALF;
@@ -439,6 +455,30 @@ __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const 
 
     st.issue(0);
     int b = 0;
+    constexpr bool COMPACT = sizeof(T) == 8 && K > 25;
+    if constexpr (COMPACT) {
+        static_assert(P / RB <= 7, "extend the switch");
+        const int nb = nsteps / RB;
+#pragma unroll 1
+        for (; b < nb; ++b) {
+            cp_async_wait<0>();
+            __syncwarp();
+            st.template gather<K, PROD>(a.f, 0);
+            __syncwarp();
+            st.issue(b + 1);
+            T* pk = m_dst + (b & 1) * RB * PARKROW;
+            switch (b % (P / RB)) {
+#define OF3D_CASE(i) case i: if constexpr (i < P / RB) strip_march_batch<T, K, P, (i < P / RB ? i : 0)>(acc, a.f, st, pk, PARKROW); break;
+                OF3D_CASE(0) OF3D_CASE(1) OF3D_CASE(2) OF3D_CASE(3) OF3D_CASE(4) OF3D_CASE(5) OF3D_CASE(6)
+#undef OF3D_CASE
+                default: break;
+            }
+            __syncthreads();
+            solve_batch(b);
+        }
+        cp_async_wait<0>();
+        return;
+    }
 #pragma unroll 1
     for (int s0 = 0; s0 < nsteps; s0 += P) {
 #pragma unroll

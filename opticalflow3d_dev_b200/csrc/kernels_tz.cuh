@@ -129,7 +129,7 @@ struct TzSrcRaw {
                     acc = fma(tt[l], tz_from_int<T>(d), acc);
                 }
             } else {
-#pragma unroll 1
+#pragma unroll 3                                                                 // (loads issued three taps ahead; the FMA chain keeps its order)
                 for (int l = 1; l <= rt; ++l) {
                     const int d = (int)*reinterpret_cast<const Tin*>(s + l * ROW) - (int)*reinterpret_cast<const Tin*>(s - l * ROW);
                     acc = fma(tt[l], tz_from_int<T>(d), acc);
