@@ -15,6 +15,7 @@
 // gradients x -> y -> z, window z -> x -> y; separable filters and per-axis clamp-to-edge commute, so this
 // equals the reference's y -> x -> z up to rounding.
 #pragma once
+#include <cstring>
 #include "common.cuh"
 #include "solve.cuh"
 
@@ -91,6 +92,31 @@ __device__ __forceinline__ void fma_acc(double& acc, double w, double v) { asm v
 __device__ __forceinline__ void fma_acc(float& acc, float w, float v) { asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc) : "f"(w), "f"(v)); }
 __device__ __forceinline__ void mul_acc(double& acc, double w, double v) { asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(acc) : "d"(w), "d"(v)); }
 __device__ __forceinline__ void mul_acc(float& acc, float w, float v) { asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(acc) : "f"(w), "f"(v)); }
+
+// Two fp32 values in one 64-bit register, for the packed FFMA2 / FMUL2 of sm_100 (fma.rn.f32x2): one issue slot per two
+// FMAs.  The fp32 marches treat two adjacent columns (z marches) or the two 32-column halves of a strip (in-plane window
+// march) as one element of this type; taps are broadcast pairs (w, w) and live in uniform registers like the fp64 taps.
+struct f32x2 {
+    unsigned long long u;
+    f32x2() = default;
+    __host__ __device__ f32x2(float a, float b) {
+        unsigned int x, y;
+        memcpy(&x, &a, 4); memcpy(&y, &b, 4);
+        u = ((unsigned long long)y << 32) | x;
+    }
+    __host__ __device__ explicit f32x2(double w) : f32x2((float)w, (float)w) {}
+    __host__ __device__ explicit f32x2(int w) : f32x2((float)w, (float)w) {}
+    __device__ __forceinline__ float lo() const { return __uint_as_float((unsigned int)u); }
+    __device__ __forceinline__ float hi() const { return __uint_as_float((unsigned int)(u >> 32)); }
+    __device__ __forceinline__ f32x2 operator-() const { f32x2 r; r.u = u ^ 0x8000000080000000ull; return r; }
+};
+__device__ __forceinline__ f32x2 operator*(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u));
+    return r;
+}
+__device__ __forceinline__ void fma_acc(f32x2& acc, f32x2 w, f32x2 v) { asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.u) : "l"(w.u), "l"(v.u)); }
+__device__ __forceinline__ void mul_acc(f32x2& acc, f32x2 w, f32x2 v) { asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(acc.u) : "l"(w.u), "l"(v.u)); }
 
 // One scatter step at static phase PH of an unrolled period P: input v (position p = o + R for the
 // output o that completes now) is accumulated into the K outputs it touches.  Returns the completed sum.

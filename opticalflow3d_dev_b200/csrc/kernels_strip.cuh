@@ -505,4 +505,111 @@ __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const 
     cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32 window x pass + y pass + solve with PACKED arithmetic (3D, nine channels).  Warp (channel ch, pair p) owns the two
+// adjacent 32-column halves [cs0 + 64 p, +32) and [cs0 + 64 p + 32, +32) of channel ch; a lane's two columns -- one per
+// half -- travel through the gather and the march as one f32x2 element: FFMA2 with broadcast tap pairs from uniform
+// registers, i.e. half the FMA instructions and half the control flow per voxel of the scalar kernel (which spends its
+// time issuing instructions, not computing: 36 % of the FFMA roof).  Staging, park and solve are the scalar kernel's.
+template <int K, int NPAIR> constexpr size_t strip_x2_warp_bytes() {
+    return (size_t)2 * kStripRB * strip_rowstride<K>() * sizeof(float) + (size_t)kStripRB * kXwRow * sizeof(f32x2);
+}
+template <int K, int NPAIR> constexpr size_t strip_x2_smem() {
+    return 9 * NPAIR * strip_x2_warp_bytes<K, NPAIR>() + (size_t)2 * kStripRB * strip_parkrow<9, 2 * NPAIR>() * sizeof(float);
+}
+
+template <int K, int P, int NPAIR>
+__global__ void __launch_bounds__(9 * NPAIR * 32, 1) strip_window_solve_x2(const StripArgs<float, K> a, const Taps<f32x2, K> f2) {
+    constexpr int RB = kStripRB, R = K / 2, NCH = 9, NW = NCH * NPAIR, TX = 64 * NPAIR, XB = kStripXB;
+    constexpr int PARKROW = strip_parkrow<NCH, 2 * NPAIR>();
+    static_assert(P >= K && P % RB == 0, "unroll period must cover the taps and be a multiple of the batch");
+    using Stage = StripStage<float, K, 1>;
+    constexpr int BUF = Stage::BUF, PITCH = Stage::PITCH, ROWSTRIDE = Stage::ROWSTRIDE;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = warp % NCH, pair = warp / NCH;
+    unsigned char* wbase = smem_raw + (size_t)warp * strip_x2_warp_bytes<K, NPAIR>();
+    float* park = reinterpret_cast<float*>(smem_raw + (size_t)NW * strip_x2_warp_bytes<K, NPAIR>());     // [2][RB][PARKROW]
+    f32x2* xw2 = reinterpret_cast<f32x2*>(wbase + 2 * BUF * sizeof(float));                              // [RB][kXwRow]
+    const StripGeom& g = a.g;
+
+    int task = blockIdx.x;
+    const int nstrips = (g.n_c + TX - 1) / TX;
+    const int strip = task % nstrips; task /= nstrips;
+    const int chunk = task % g.n_chunks;
+    const int o = task / g.n_chunks;
+    const int cs0 = strip * TX;
+    const int m0 = chunk * g.chunk;
+    const int nout = min(m0 + g.chunk, g.n_m) - m0;
+    const int nsteps = (nout + 2 * R + P - 1) / P * P;
+
+    Stage st0, st1;                                           // (their own gathered-row buffers are not used)
+    st0.init(reinterpret_cast<float*>(wbase), cs0 + 64 * pair, m0 - R, g);
+    st1.init(reinterpret_cast<float*>(wbase) + BUF, cs0 + 64 * pair + 32, m0 - R, g);
+    st0.src[0] = st1.src[0] = a.in[0] + (int64_t)o * g.stride_o + (int64_t)ch * g.vol;
+    float* const m_dst = park + ch * TX + 64 * pair + lane;
+    f32x2 acc[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) acc[i] = f32x2(0);
+
+    auto solve_batch = [&](int bb) {
+#pragma unroll 1
+        for (int unit = warp; unit < RB * TX / 32; unit += NW)
+            solve_unit_voxels<float, NCH, TX, R>(park, PARKROW, bb, unit, lane, cs0, nout, g.n_c, (int64_t)o * g.stride_o, g.stride_m, m0,
+                                                 a.vx, a.vy, a.vz, a.rel, 0);
+    };
+
+    st0.issue(0);
+    st1.issue(0);
+    int b = 0;
+#pragma unroll 1
+    for (int s0 = 0; s0 < nsteps; s0 += P) {
+#pragma unroll
+        for (int bi = 0; bi < P / RB; ++bi, ++b) {
+            cp_async_wait<0>();
+            __syncwarp();                                                     // this warp's rows of batch b have landed
+            {
+                // ---------------- gather along x, both halves at once: lane (row g_r, block g_b) -> 8 consecutive outputs
+                const int g_r = lane >> 2, g_b = lane & 3;
+                const float* r0 = st0.rows + g_r * ROWSTRIDE + g_b;
+                const float* r1 = st1.rows + g_r * ROWSTRIDE + g_b;
+                f32x2 ga[XB];
+#pragma unroll
+                for (int mm = 0; mm < XB + K - 1; ++mm) {
+                    const f32x2 v(r0[(mm & 7) * PITCH + (mm >> 3)], r1[(mm & 7) * PITCH + (mm >> 3)]);
+#pragma unroll
+                    for (int i = 0; i < XB; ++i) {
+                        const int k = mm - i;
+                        if (k >= 0 && k < K) {
+                            const f32x2 w = f2.w[k > R ? K - 1 - k : k];      // symmetric window: half of the taps
+                            if (k == 0) mul_acc(ga[i], w, v); else fma_acc(ga[i], w, v);
+                        }
+                    }
+                }
+                f32x2* d = xw2 + g_r * kXwRow + g_b * (XB + 1);
+#pragma unroll
+                for (int i = 0; i < XB; ++i) d[i] = ga[i];
+            }
+            __syncwarp();                                                     // gathered rows visible; input rows free
+            st0.issue(b + 1);                                                 // prefetch (clamped addresses: always valid)
+            st1.issue(b + 1);
+            // ---------------- march along y: output j = s - 2R lives in park row j mod RB of buffer b & 1
+            {
+                float* pk = m_dst + (b & 1) * RB * PARKROW;
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const f32x2 res = ring_push<f32x2, K, P, 1>(acc, f2, xw2[r * kXwRow + lane + lane / 8], bi * RB + r);
+                    constexpr int kBias = (2 * R + RB - 1) / RB * RB;
+                    float* q = pk + ((r + kBias - 2 * R) % RB) * PARKROW;
+                    q[0] = res.lo();
+                    q[32] = res.hi();
+                }
+            }
+            __syncthreads();                                                  // one batch of outputs parked by all channels
+            solve_batch(b);
+        }
+    }
+    cp_async_wait<0>();
+}
+
 }  // namespace of3d
