@@ -297,6 +297,86 @@ __global__ void __launch_bounds__(WPB * 32) strip_conv2(const Conv2Args<T, KG, K
     cp_async_wait<0>();
 }
 
+// Two gradients from ONE staged input (3D: dy = D_y S_x A and dx = S_y D_x A share A; 2D: the same on Ic): the rows are
+// staged once with the halo of the wider x filter, gathered twice and marched twice.  Saves one read of the input volume
+// and one launch against two strip_conv2 launches.  outA = march fa1 (KR taps, antisymmetric D) of gather fg1 (KS taps, S);
+// outB = march fa2 (KS taps, S) of gather fg2 (KR taps, antisymmetric D).
+template <typename T, int KR, int KS>
+struct Conv2DualArgs {
+    StripGeom g;
+    Taps<T, KR> fD;
+    Taps<T, KS> fS;
+    const T* in;
+    T* out_dy;      // D_y S_x in
+    T* out_dx;      // S_y D_x in
+};
+
+template <typename T, int KR, int KS, int WPB, bool V16 = false>
+__global__ void __launch_bounds__(WPB * 32) strip_conv2_dual(const Conv2DualArgs<T, KR, KS> a) {
+    constexpr int RB = kStripRB, R = KR / 2, RS = KS / 2, P = (KR + RB - 1) / RB * RB;
+    using Stage = typename std::conditional<V16, StripStage16<typename std::conditional<V16, T, double>::type, KR>, StripStage<T, KR, 1, 2>>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const StripGeom& g = a.g;
+    int64_t task = (int64_t)blockIdx.x * WPB + warp;
+    const int nstrips = (g.n_c + 31) / 32;
+    if (task >= (int64_t)nstrips * g.n_chunks * g.n_o) return;
+    const int strip = (int)(task % nstrips); task /= nstrips;
+    const int chunk = (int)(task % g.n_chunks);
+    const int o = (int)(task / g.n_chunks);
+    const int cw0 = strip * 32;
+    const int m0 = chunk * g.chunk;
+    const int nout = min(m0 + g.chunk, g.n_m) - m0;
+    const int nsteps = (nout + 2 * R + P - 1) / P * P;
+    const unsigned nvalid = (cw0 + lane < g.n_c) ? (unsigned)nout : 0u;
+
+    Stage st;
+    st.init(reinterpret_cast<T*>(smem_raw) + warp * Stage::elems, cw0, m0 - R, g);
+    if constexpr (V16) st.src = a.in + (int64_t)o * g.stride_o;
+    else st.src[0] = a.in + (int64_t)o * g.stride_o;
+    const int64_t obase = (int64_t)o * g.stride_o + cw0 + lane;
+    T* const oy = a.out_dy + obase;
+    T* const ox = a.out_dx + obase;
+
+    T accY[P], accX[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) { accY[i] = T(0); accX[i] = T(0); }
+
+    st.issue(0);
+    st.issue(1);
+    int b = 0;
+#pragma unroll 1
+    for (int s0 = 0; s0 < nsteps; s0 += P) {
+#pragma unroll
+        for (int bi = 0; bi < P / RB; ++bi, ++b) {
+            cp_async_wait<1>();                                               // batch b has landed, b + 1 is in flight
+            __syncwarp();
+            if constexpr (V16) { st.fix_edges(b); st.template gather<KS, 1>(a.fS, b); }
+            else st.template gather<KS, false>(a.fS, 0, b);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {                                     // dy = D_y (S_x in): row m0 + s - 2R
+                const int s = s0 + bi * RB + r;
+                const T res = ring_push<T, KR, P, -1>(accY, a.fD, st.gathered(r), bi * RB + r);
+                if ((unsigned)(s - 2 * R) < nvalid) oy[(int64_t)(m0 + s - 2 * R) * g.stride_m] = res;
+            }
+            __syncwarp();                                                     // gathered rows consumed
+            if constexpr (V16) st.template gather<KR, -1>(a.fD, b);
+            else st.template gather<KR, false>(a.fD, 0, b);
+            __syncwarp();
+            st.issue(b + 2);                                                  // into the buffer both gathers have consumed
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {                                     // dx = S_y (D_x in): row m0 + s - R - RS
+                const int s = s0 + bi * RB + r;
+                const T res = ring_push<T, KS, P, 1>(accX, a.fS, st.gathered(r), bi * RB + r);
+                if ((unsigned)(s - R - RS) < nvalid) ox[(int64_t)(m0 + s - R - RS) * g.stride_m] = res;
+            }
+            __syncwarp();
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Window x pass + y pass + solve.  A block has NCH * NHALF warps: warp (channel ch, half h) owns columns
 // [cs0 + 32 h, +32) of channel ch.  After gather and march a completed row is parked in shared memory; ONE block
