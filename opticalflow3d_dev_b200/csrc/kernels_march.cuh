@@ -122,12 +122,16 @@ __device__ __forceinline__ void mul_acc(f32x2& acc, f32x2 w, f32x2 v) { asm vola
 // output o that completes now) is accumulated into the K outputs it touches.  Returns the completed sum.
 // SYM = +1 / -1: the taps are (anti)symmetric, w[K-1-k] = +-w[k] (checked by the host, fast_supported): only the first
 // R + 1 of them are read, which halves the registers the taps occupy.
-template <typename T, int K, int P, int SYM = 0>
+// WARM: the step is one of the first K - 1 of a march (step index == ph): tap k feeds the output that lies ph - k planes
+// after the first one, so the taps k > ph only feed outputs before the range -- a triangle of K (K - 1) / 2 useless FMAs
+// per march, a third of the work of a 37-tap march over 64 planes -- and are skipped.
+template <typename T, int K, int P, int SYM = 0, bool WARM = false>
 __device__ __forceinline__ T ring_push(T (&acc)[P], const Taps<T, K>& f, const T v, const int ph) {
     constexpr int R = K / 2;
     const T vn = SYM < 0 ? -v : v;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
+        if (WARM && k > ph) continue;
         const int slot = (ph + R - k + 2 * P) % P;   // constant after unrolling
         const bool mirror = SYM != 0 && k > R;
         const T w = f.w[mirror ? K - 1 - k : k];

@@ -144,8 +144,27 @@ __global__ void __launch_bounds__((9 * NG + 1) * 32, MINB) march_window_tma(cons
     char* optr = reinterpret_cast<char*>(a.out + (int64_t)ch * g.vol + (int64_t)t.y * g.stride_other + lane0 + lane) +
                  ((int64_t)(t.c0 - g.m_begin) - 2 * R) * stride_bytes;
     int it = 0;
+    // first period: the warm-up triangle of the ring is skipped (ring_push<..., WARM>)
+#pragma unroll
+    for (int sg = 0; sg < P / ZT; ++sg) {
+        const int slot = it % ST;
+        mbar_wait(bar_s + 8 * slot, (it / ST) & 1);
+        const T* pa = sa + slot * kStageElems;
+        const T* pb = sb + slot * kStageElems;
+#pragma unroll
+        for (int r = 0; r < ZT; ++r) {
+            const int ph = sg * ZT + r;
+            const T v = pa[r * 4 * TX] * pb[r * 4 * TX];
+            const T res = ring_push<T, K, P, 1, true>(acc, a.f, v, ph);
+            if ((unsigned)(ph - 2 * R) < nvalid) *reinterpret_cast<T*>(optr) = res;
+            optr += stride_bytes;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_s + 8 * (ST + slot));
+        if (++it >= t.nstages) return;
+    }
 #pragma unroll 1
-    for (int s0 = 0;; s0 += P) {
+    for (int s0 = P;; s0 += P) {
 #pragma unroll
         for (int sg = 0; sg < P / ZT; ++sg) {
             const int slot = it % ST;
