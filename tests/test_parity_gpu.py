@@ -113,6 +113,8 @@ def test_golden_fp32_mode(name):
     ((13, 20, 50, 60), (3, 2, 6), np.uint16),       # cfg3 parameters
     ((19, 6, 20, 130), (3, 3, 8), np.float32),      # cfg5 parameters; window wider than z and y
     ((7, 3, 5, 4), (1, 1, 4), np.uint8),            # volume smaller than every filter
+    ((7, 10, 24, 32), (1, 1, 2), np.uint8),         # uint8 frames with 16-byte rows: temporal stage fused into the z march
+    ((13, 12, 20, 64), (1, 2, 2), np.uint16),       # 13-frame window: run-time temporal loop of the fused march
     ((7, 1, 40, 33), (2, 1, 3), np.float64),        # single z plane through the 3D entry point
     ((5, 9, 31, 37), (0.7, 0.5, 1.2), np.int16),    # sub-pixel sigmas: 3-tap S, 5-tap T
 ])
