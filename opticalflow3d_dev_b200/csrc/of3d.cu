@@ -966,7 +966,9 @@ static int slab_run(of3d_ctx* c, const void* const* frames_ext, const void* ic_e
     std::vector<int64_t> starts, late;
     for (int64_t a = own_lo; a < own_lo + own_n; a += chunk) {
         const int64_t b = std::min(own_lo + own_n, a + chunk);
-        const bool interior = a - H >= own_lo && b + H <= own_lo + own_n;
+        // a chunk waits for the exchange only if it reaches into a halo that exists (none at the ends of the volume)
+        const bool need_lo = own_lo > 0 && a - H < own_lo, need_hi = own_lo + own_n < nz_ext && b + H > own_lo + own_n;
+        const bool interior = !need_lo && !need_hi;
         (c->halo_pending && !interior ? late : starts).push_back(a);
     }
     const size_t n_first = starts.size();

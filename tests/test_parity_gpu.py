@@ -387,7 +387,7 @@ def test_rel_f32_flag_is_one_rounding_of_the_float64_value():
     assert t32[3].dtype == torch.float32 and np.array_equal(t32[3].cpu().numpy(), r32[3])
 
 
-@pytest.mark.parametrize('shape', [(7, 21, 50, 200), (7, 3, 20, 64), (7, 1, 16, 68), (7, 9, 12, 36)])
+@pytest.mark.parametrize('shape', [(7, 21, 50, 200), (7, 3, 20, 64), (7, 1, 16, 68), (7, 1, 16, 64), (7, 9, 12, 36)])
 @pytest.mark.parametrize('precision', ['fp64', 'fp32'])
 def test_tma_window_march_equals_cp_async_march(precision, shape, monkeypatch):
     """The TMA-fed window z march (tensor-map tiles, padded gradient volumes) and the cp.async march it replaces do the
