@@ -54,8 +54,21 @@ def _sample_format(dtype):
     raise TypeError('tiffio.imwrite: unsupported dtype %s' % dtype)
 
 
-def imwrite(path, data, photometric='minisblack', bigtiff=None, description=None):
-    """Write a 2D array as one page or an N-D array as a multi-page TIFF (one page per leading-axis plane)."""
+_WRITE_POOL = None
+
+
+def _write_pool(threads):
+    global _WRITE_POOL
+    if _WRITE_POOL is None or _WRITE_POOL._max_workers < threads:
+        from concurrent.futures import ThreadPoolExecutor
+        _WRITE_POOL = ThreadPoolExecutor(max_workers=max(threads, 8))
+    return _WRITE_POOL
+
+
+def imwrite(path, data, photometric='minisblack', bigtiff=None, description=None, threads=1):
+    """Write a 2D array as one page or an N-D array as a multi-page TIFF (one page per leading-axis plane).
+    threads > 1: the pixel data of the pages are written by that many threads with positioned writes (the layout of the
+    file is known up front); a RAM-disk or page-cache write is a memcpy at ~1.6 GB/s per thread."""
     if photometric not in ('minisblack', None):
         raise ValueError('only photometric="minisblack" is supported')
     a = np.asarray(data)
@@ -82,7 +95,7 @@ def imwrite(path, data, photometric='minisblack', bigtiff=None, description=None
     off_size = 8 if bigtiff else 4
     entry_size = 20 if bigtiff else 12
 
-    def ifd_bytes(tags, ifd_offset, next_offset_placeholder=0):
+    def ifd_bytes(tags, ifd_offset):
         """tags: list of (tag, type, count, payload bytes).  Values too large for the slot go after the IFD."""
         n = len(tags)
         head = struct.pack('<Q', n) if bigtiff else struct.pack('<H', n)
@@ -100,40 +113,69 @@ def imwrite(path, data, photometric='minisblack', bigtiff=None, description=None
             entries += e
         return head, entries, extra
 
-    with open(path, 'wb') as fh:
-        if bigtiff:
-            fh.write(b'II' + struct.pack('<HHHQ', 43, 8, 0, 16))
-            pos = 16
-        else:
-            fh.write(b'II' + struct.pack('<HI', 42, 8))
-            pos = 8
-        long_t = 16 if bigtiff else 4
-        for i in range(npages):
-            # layout of a page: IFD (+ overflow values) then pixel data, both word aligned
-            def tags_for(data_off):
-                t = [(256, 4, 1, struct.pack('<I', nx)), (257, 4, 1, struct.pack('<I', ny)),
-                     (258, 3, 1, struct.pack('<H', bits)), (259, 3, 1, struct.pack('<H', 1)),
-                     (262, 3, 1, struct.pack('<H', 1)),
-                     (273, long_t, 1, struct.pack(off_fmt, data_off)),
-                     (277, 3, 1, struct.pack('<H', 1)), (278, 4, 1, struct.pack('<I', ny)),
-                     (279, long_t, 1, struct.pack(off_fmt, page_bytes)),
-                     (282, 5, 1, struct.pack('<II', 1, 1)), (283, 5, 1, struct.pack('<II', 1, 1)),
-                     (296, 3, 1, struct.pack('<H', 1)), (339, 3, 1, struct.pack('<H', sf))]
-                if i == 0:
-                    t += [(270, 2, len(desc), desc), (305, 2, len(software), software)]
-                return t
-            head, entries, extra = ifd_bytes(tags_for(0), pos)
-            ifd_len = len(head) + len(entries) + off_size + len(extra)
-            data_off = (pos + ifd_len + 15) // 16 * 16
-            head, entries, extra = ifd_bytes(tags_for(data_off), pos)
-            next_ifd = 0 if i == npages - 1 else (data_off + page_bytes + 15) // 16 * 16
-            fh.write(head + entries + struct.pack(off_fmt, next_ifd) + extra)
-            fh.write(b'\0' * (data_off - pos - ifd_len))
-            fh.write(memoryview(a[i]).cast('B'))
-            pos = data_off + page_bytes
-            if next_ifd:
-                fh.write(b'\0' * (next_ifd - pos))
-                pos = next_ifd
+    long_t = 16 if bigtiff else 4
+
+    def tags_for(i, data_off):
+        t = [(256, 4, 1, struct.pack('<I', nx)), (257, 4, 1, struct.pack('<I', ny)),
+             (258, 3, 1, struct.pack('<H', bits)), (259, 3, 1, struct.pack('<H', 1)),
+             (262, 3, 1, struct.pack('<H', 1)),
+             (273, long_t, 1, struct.pack(off_fmt, data_off)),
+             (277, 3, 1, struct.pack('<H', 1)), (278, 4, 1, struct.pack('<I', ny)),
+             (279, long_t, 1, struct.pack(off_fmt, page_bytes)),
+             (282, 5, 1, struct.pack('<II', 1, 1)), (283, 5, 1, struct.pack('<II', 1, 1)),
+             (296, 3, 1, struct.pack('<H', 1)), (339, 3, 1, struct.pack('<H', sf))]
+        if i == 0:
+            t += [(270, 2, len(desc), desc), (305, 2, len(software), software)]
+        return t
+
+    # layout of a page: IFD (+ overflow values) then pixel data, both 16-byte aligned; known without touching the data
+    header = b'II' + (struct.pack('<HHHQ', 43, 8, 0, 16) if bigtiff else struct.pack('<HI', 42, 8))
+    pos = len(header)
+    meta, data_offs = [], []                                  # (offset, bytes) of every IFD blob; data offset of every page
+    for i in range(npages):
+        head, entries, extra = ifd_bytes(tags_for(i, 0), pos)
+        ifd_len = len(head) + len(entries) + off_size + len(extra)
+        data_off = (pos + ifd_len + 15) // 16 * 16
+        head, entries, extra = ifd_bytes(tags_for(i, data_off), pos)
+        next_ifd = 0 if i == npages - 1 else (data_off + page_bytes + 15) // 16 * 16
+        meta.append((pos, head + entries + struct.pack(off_fmt, next_ifd) + extra))
+        data_offs.append(data_off)
+        pos = next_ifd if next_ifd else data_off + page_bytes
+    total = pos
+
+    threads = max(1, min(int(threads), npages))
+    if threads == 1:
+        with open(path, 'wb') as fh:
+            fh.write(header)
+            at = len(header)
+            for i in range(npages):
+                off, blob = meta[i]
+                fh.write(b'\0' * (off - at) + blob)
+                at = off + len(blob)
+                fh.write(b'\0' * (data_offs[i] - at))
+                fh.write(memoryview(a[i]).cast('B'))
+                at = data_offs[i] + page_bytes
+        return
+    fd = os.open(os.fspath(path), os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o666)
+    try:
+        os.ftruncate(fd, total)                               # gaps between the pieces read back as zeros
+        os.pwrite(fd, header, 0)
+        for off, blob in meta:
+            os.pwrite(fd, blob, off)
+
+        def put(lo, hi):
+            for i in range(lo, hi):
+                mv = memoryview(a[i]).cast('B')
+                done = 0
+                while done < page_bytes:
+                    done += os.pwrite(fd, mv[done:], data_offs[i] + done)
+
+        cuts = [npages * k // threads for k in range(threads + 1)]
+        futs = [_write_pool(threads).submit(put, cuts[k], cuts[k + 1]) for k in range(threads)]
+        for f in futs:
+            f.result()
+    finally:
+        os.close(fd)
 
 
 # ------------------------------------------------------------------------------------------ reader

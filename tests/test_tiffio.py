@@ -20,6 +20,14 @@ def test_roundtrip_multipage(tmp_path, dtype):
     assert np.array_equal(tiffio.imread(p), a)
 
 
+def test_threaded_write_is_byte_identical(tmp_path):
+    a = (np.random.default_rng(1).normal(size=(9, 13, 17)) * 50 + 100).astype(np.float32)
+    for big in (False, True):
+        tiffio.imwrite(tmp_path / 's.tiff', a, bigtiff=big)
+        tiffio.imwrite(tmp_path / 'p.tiff', a, bigtiff=big, threads=4)
+        assert (tmp_path / 's.tiff').read_bytes() == (tmp_path / 'p.tiff').read_bytes()
+
+
 def test_imagej_hyperstack_and_memmap(tmp_path):
     a = np.arange(4 * 3 * 6 * 7).reshape(4, 3, 6, 7).astype(np.uint16)
     p = tmp_path / 'ij.tif'
