@@ -586,6 +586,138 @@ __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2D: products + window x pass + y pass + solve with the three gradient frames staged ONCE per block.
+// strip_window_solve<.., PROD> lets every (channel, half) warp stage the two gradients of its own product: ten staged
+// copies of three frames, 151 KB of shared memory for ten warps, which is all an SM then holds (47 % FP64 pipe).  Here the
+// block's 5 NQ warps fetch one copy of the RB rows x (32 NQ + K - 1) columns of {dt, dx, dy} together (blocked-transposed
+// rows as in StripStage, element-wise cp.async with clamped source addresses = mode='nearest'), and warp (channel ch,
+// quarter q) forms its product while it gathers.  The staging is double-buffered across the batch barrier that already
+// exists: batch b + 1 is issued at the top of batch b (its buffer was last read by the gathers of b - 1, which every warp
+// finished before barrier b - 1), each warp waits for its own copies right before barrier b, and the barrier publishes
+// them -- no second barrier, one batch time (thousands of cycles) of prefetch distance.  20 warps (5,5,5,5) at 96 registers.
+// The arithmetic is strip_window_solve<.., PROD>'s, operation for operation (bit-identical results).
+template <typename T, int K, int NQ>
+struct Prod2D {
+    static constexpr int NCH = 5, NW = NCH * NQ, TX = 32 * NQ, RL = TX + K - 1, NI = (RL + 7) / 8;
+    static constexpr int PITCH = NI | 1;
+    static constexpr int ROWSTRIDE = (8 * PITCH + 11) / 16 * 16 + 4;   // = 4 (mod 16): see strip_rowstride
+    static constexpr int VOLBUF = kStripRB * ROWSTRIDE, BUF = 3 * VOLBUF;
+    static constexpr int PARKROW = strip_parkrow<NCH, NQ>();
+    static constexpr size_t smem = (size_t)(2 * BUF + NW * kStripRB * kXwRow + 2 * kStripRB * PARKROW) * sizeof(T);
+};
+
+template <typename T, int K, int P, int NQ>
+__global__ void __launch_bounds__(5 * NQ * 32, 1) strip_window_solve_2d(const StripArgs<T, K> a) {
+    using L = Prod2D<T, K, NQ>;
+    constexpr int RB = kStripRB, XB = kStripXB, R = K / 2, NCH = 5, NW = L::NW, TX = L::TX;
+    constexpr int PITCH = L::PITCH, ROWSTRIDE = L::ROWSTRIDE, PARKROW = L::PARKROW;
+    static_assert(P >= K && P % RB == 0, "unroll period must cover the taps and be a multiple of the batch");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* const stage = reinterpret_cast<T*>(smem_raw);                         // [2][3][RB][ROWSTRIDE]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = warp % NCH, q = warp / NCH;
+    T* const xw = stage + 2 * L::BUF + warp * RB * kXwRow;                   // [RB][kXwRow], private to the warp
+    T* const park = stage + 2 * L::BUF + NW * RB * kXwRow;                   // [2][RB][PARKROW], shared by the block
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    const StripGeom& g = a.g;
+
+    int task = blockIdx.x;
+    const int nstrips = (g.n_c + TX - 1) / TX;
+    const int strip = task % nstrips; task /= nstrips;
+    const int chunk = task % g.n_chunks;
+    const int o = task / g.n_chunks;
+    const int cs0 = strip * TX;
+    const int m0 = chunk * g.chunk;
+    const int nout = min(m0 + g.chunk, g.n_m) - m0;
+    const int nsteps = (nout + 2 * R + P - 1) / P * P;
+    const int64_t plane_off = (int64_t)o * g.stride_o;
+
+    // a task = 8 consecutive elements (one per lane of a quarter-warp) of one row of one gradient
+    auto issue = [&](int b) {
+        constexpr int NTASK = 3 * RB * L::NI;
+        const int l8 = lane & 7;
+#pragma unroll 1
+        for (int j = 0; j < (NTASK + 4 * NW - 1) / (4 * NW); ++j) {
+            const int tk = j * 4 * NW + warp * 4 + (lane >> 3);
+            const int i = tk % L::NI, rv = tk / L::NI, r = rv % RB, v = rv / RB;
+            const int e = 8 * i + l8;
+            if (tk < NTASK && (L::RL % 8 == 0 || e < L::RL)) {
+                const int m = max(0, min(m0 - R + b * RB + r, g.n_m - 1));
+                const int c = max(0, min(cs0 - R + e, g.n_c - 1));
+                cp_async_elem<T>(stage_s + (uint32_t)(((b & 1) * L::BUF + v * L::VOLBUF + r * ROWSTRIDE + l8 * PITCH + i) * sizeof(T)),
+                                 a.in[v] + plane_off + (int64_t)m * g.stride_m + c);
+            }
+        }
+        cp_async_commit();
+    };
+
+    // channel -> gradient pair {xx,xy,yy,tx,ty}; a.in = {dt, dx, dy}   (calc_flow.py:133-141)
+    const int ia = (ch == 2 || ch == 4) ? 2 : 1;
+    const int ib = ch == 0 ? 1 : (ch <= 2 ? 2 : 0);
+    const int g_r = lane >> 2, g_b = lane & 3;
+    const int goff_a = ia * L::VOLBUF + g_r * ROWSTRIDE + g_b + 4 * q;      // element 32 q + 8 g_b of row g_r
+    const int goff_d = (ib - ia) * L::VOLBUF;
+    T* const m_dst = park + ch * TX + 32 * q + lane;
+    T acc[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) acc[i] = T(0);
+
+    auto solve_batch = [&](int bb) {
+#pragma unroll 1
+        for (int unit = warp; unit < RB * TX / 32; unit += NW)
+            solve_unit_voxels<T, NCH, TX, R>(park, PARKROW, bb, unit, lane, cs0, nout, g.n_c, plane_off, g.stride_m, m0,
+                                             a.vx, a.vy, a.vz, a.rel, a.rel_f32);
+    };
+
+    issue(0);
+    cp_async_wait<0>();
+    __syncthreads();
+    int b = 0;
+#pragma unroll 1
+    for (int s0 = 0; s0 < nsteps; s0 += P) {
+#pragma unroll
+        for (int bi = 0; bi < P / RB; ++bi, ++b) {
+            issue(b + 1);                                                     // clamped addresses: always valid
+            {
+                // ---------------- products + gather along x: lane (row g_r, block g_b) -> 8 consecutive outputs
+                const T* sa = stage + (b & 1) * L::BUF + goff_a;
+                T ga[XB];
+#pragma unroll
+                for (int i = 0; i < XB; ++i) ga[i] = T(0);
+#pragma unroll
+                for (int mm = 0; mm < XB + K - 1; ++mm) {
+                    T v = sa[(mm & 7) * PITCH + (mm >> 3)];
+                    v *= sa[goff_d + (mm & 7) * PITCH + (mm >> 3)];
+#pragma unroll
+                    for (int i = 0; i < XB; ++i) {
+                        const int k = mm - i;
+                        if (k >= 0 && k < K) ga[i] = fma(a.f.w[k], v, ga[i]);
+                    }
+                }
+                T* d = xw + g_r * kXwRow + g_b * (XB + 1);
+#pragma unroll
+                for (int i = 0; i < XB; ++i) d[i] = ga[i];
+            }
+            __syncwarp();                                                     // gathered rows visible to the warp
+            // ---------------- march along y: output j = s - 2R lives in park row j mod RB of buffer b & 1
+            {
+                T* pk = m_dst + (b & 1) * RB * PARKROW;
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const T res = ring_push<T, K, P, 1>(acc, a.f, xw[r * kXwRow + lane + lane / 8], bi * RB + r);
+                    constexpr int kBias = (2 * R + RB - 1) / RB * RB;
+                    pk[((r + kBias - 2 * R) % RB) * PARKROW] = res;
+                }
+            }
+            cp_async_wait<0>();                                               // this warp's pieces of batch b + 1 have landed
+            __syncthreads();                                                  // batch b parked, batch b + 1 staged, by all warps
+            solve_batch(b);                                                   // the RB x TX outputs of batch b
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp32 window x pass + y pass + solve with PACKED arithmetic (3D, nine channels).  Warp (channel ch, pair p) owns the two
 // adjacent 32-column halves [cs0 + 64 p, +32) and [cs0 + 64 p + 32, +32) of channel ch; a lane's two columns -- one per
 // half -- travel through the gather and the march as one f32x2 element: FFMA2 with broadcast tap pairs from uniform

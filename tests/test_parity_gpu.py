@@ -332,6 +332,30 @@ def test_flow2d_batch_equals_per_window_calls(shape, sig, precision, dtype):
         cf.calc_flow2D_timelapse(img[:kt - 1], *sig)
 
 
+@pytest.mark.parametrize('shape,sig,precision', [
+    ((7, 70, 300), (1.5, 1, 4), 'fp64'),           # 25 window taps, ragged last 128-column strip
+    ((7, 41, 129), (1, 1, 2), 'fp64'),             # 13 taps, one column into the second strip, odd row length
+    ((7, 90, 64), (2, 1, 3), 'fp64'),              # 19 taps, frame narrower than a strip
+    ((7, 130, 257), (1.5, 1, 4), 'fp32'),
+    ((7, 64, 200), (1, 1, 8), 'fp32'),             # 49 taps (fp32 only: the fp64 ring does not fit 20 warps)
+])
+def test_flow2d_block_staged_kernel_equals_warp_staged_kernel(shape, sig, precision, monkeypatch):
+    """strip_window_solve_2d (gradients staged once per block, 20 warps) does the arithmetic of the warp-staged
+    strip_window_solve<PROD> operation for operation: bit-identical flow, and the oracle's flow within the bar."""
+    from opticalflow3d_dev_b200.synth import make_stack
+    cf = _cf()
+    img = make_stack(shape, seed=71, dtype=np.uint16)
+    new = cf.calc_flow2D(img, *sig, precision=precision)
+    monkeypatch.setenv('OF3D_2D_WARPSTAGE', '1')
+    old = cf.calc_flow2D(img, *sig, precision=precision)
+    monkeypatch.delenv('OF3D_2D_WARPSTAGE')
+    for n, o in zip(new, old):
+        assert np.array_equal(n, o, equal_nan=True)
+    if precision == 'fp64':
+        ref = orc.lk_flow2d(img, *sig)
+        assert_flow_close(new[:2], ref[:2], ref[2], 1e-9, '2d block-staged')
+
+
 def test_tap_counts_without_specialised_kernels_fall_back_to_generic():
     """wSig = 9 -> 55 window taps, xyzSig = 5 -> 31 gradient taps: no marching/strip instantiation; the generic
     kernels must take over transparently and still match the oracle."""
