@@ -141,6 +141,33 @@ __device__ __forceinline__ T ring_push(T (&acc)[P], const Taps<T, K>& f, const T
     return acc[(ph - R + 2 * P) % P];
 }
 
+// The same step in a stage at the TAIL of a march, with the useless taps skipped in groups of G behind warp-uniform
+// branches.  Step s lies d = s - nout steps into the tail; tap k feeds the output s - k planes after the first one of the
+// range, so the taps k <= d only feed outputs beyond it: the mirror image of the warm-up triangle, K (K - 1) / 2 FMAs at a
+// run-time phase of the unrolled period.  d0 = d of the FIRST step of the stage (one set of tests per stage: a group is
+// skipped when none of its taps is useful in any step of the stage).  A skipped group leaves its accumulators stale: they
+// belong to outputs outside the range, which are never stored, and a slot is re-initialised by tap 0 of the output that
+// claims it next.
+template <typename T, int K, int P, int SYM, int G>
+__device__ __forceinline__ T ring_push_tail(T (&acc)[P], const Taps<T, K>& f, const T v, const int ph, const int d0) {
+    constexpr int R = K / 2;
+    const T vn = SYM < 0 ? -v : v;
+#pragma unroll
+    for (int kb = 0; kb < K; kb += G) {
+        if (d0 < kb + G - 1) {                              // kb + G - 1 > d0: the group holds a useful tap in this stage
+#pragma unroll
+            for (int k = kb; k < (kb + G < K ? kb + G : K); ++k) {
+                const int slot = (ph + R - k + 2 * P) % P;
+                const bool mirror = SYM != 0 && k > R;
+                const T w = f.w[mirror ? K - 1 - k : k];
+                if (k == 0) mul_acc(acc[slot], w, v);
+                else fma_acc(acc[slot], w, mirror ? vn : v);
+            }
+        }
+    }
+    return acc[(ph - R + 2 * P) % P];
+}
+
 // ------------------------------------------------------------------------------------------------
 // Products + window z pass (calc_flow.py:300-313, z passes): one warp per (channel, y row, 32 x columns, z chunk);
 // the product of the channel's two gradient volumes is formed as the values come out of the prefetch ring.
@@ -151,6 +178,7 @@ struct WindowArgs {
     const T* in[4];   // gradient volumes {dt, dx, dy, dz}
     T* out;           // channel-major output {xx,xy,xz,yy,yz,zz,tx,ty,tz}
     int nch;          // 9
+    int edge_skip;    // TMA march: skip the useless taps of the last 2R steps (0: OF3D_NO_TAIL_SKIP, for A/B measurements)
 };
 
 // channel -> gradient pair; index into {dt,dx,dy,dz}

@@ -53,6 +53,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int 
 // windows whose accumulator ring alone needs 80-112 registers.
 constexpr int kTmaZT = 8;        // z steps per stage
 constexpr int kTmaStages = 4;
+constexpr int kEdgeGroup = 8;    // taps per uniform branch at the tail of a march (ring_push_tail)
 
 template <typename T, int NG>
 constexpr size_t window_tma_smem() { return (size_t)kTmaStages * 4 * kTmaZT * 32 * NG * sizeof(T) + 2 * kTmaStages * 8; }
@@ -165,19 +166,37 @@ __global__ void __launch_bounds__((9 * NG + 1) * 32, MINB) march_window_tma(cons
     }
 #pragma unroll 1
     for (int s0 = P;; s0 += P) {
+        // step s of the march lies d = s - nout steps into the tail: its taps k <= d only feed outputs beyond the range.
+        // A stage whose first step has d > 0 runs the copy of the body that skips them in groups (ring_push_tail).
+        // edge_skip == 0 (OF3D_NO_TAIL_SKIP): never in the tail
+        const int dbase = a.edge_skip ? s0 - t.nout : -(1 << 20);
 #pragma unroll
         for (int sg = 0; sg < P / ZT; ++sg) {
             const int slot = it % ST;
             mbar_wait(bar_s + 8 * slot, (it / ST) & 1);
             const T* pa = sa + slot * kStageElems;
             const T* pb = sb + slot * kStageElems;
+            const int d0 = dbase + sg * ZT;
+            // (windows longer than 25 taps: one copy of the body, the group tests always run -- two copies of a 56 x 49
+            // scatter are more than the compiler unrolls, and the accumulator ring ends up in local memory)
+            if (K <= 25 && d0 <= 0) {
 #pragma unroll
-            for (int r = 0; r < ZT; ++r) {
-                const int ph = sg * ZT + r;
-                const T v = pa[r * 4 * TX] * pb[r * 4 * TX];
-                const T res = ring_push<T, K, P, 1>(acc, a.f, v, ph);
-                if ((unsigned)(s0 + ph - 2 * R) < nvalid) *reinterpret_cast<T*>(optr) = res;
-                optr += stride_bytes;
+                for (int r = 0; r < ZT; ++r) {
+                    const int ph = sg * ZT + r;
+                    const T v = pa[r * 4 * TX] * pb[r * 4 * TX];
+                    const T res = ring_push<T, K, P, 1>(acc, a.f, v, ph);
+                    if ((unsigned)(s0 + ph - 2 * R) < nvalid) *reinterpret_cast<T*>(optr) = res;
+                    optr += stride_bytes;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < ZT; ++r) {
+                    const int ph = sg * ZT + r;
+                    const T v = pa[r * 4 * TX] * pb[r * 4 * TX];
+                    const T res = ring_push_tail<T, K, P, 1, kEdgeGroup>(acc, a.f, v, ph, d0);
+                    if ((unsigned)(s0 + ph - 2 * R) < nvalid) *reinterpret_cast<T*>(optr) = res;
+                    optr += stride_bytes;
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_s + 8 * (ST + slot));
