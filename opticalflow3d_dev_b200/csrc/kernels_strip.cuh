@@ -764,9 +764,19 @@ __global__ void __launch_bounds__(9 * NPAIR * 32, 1) strip_window_solve_x2(const
 #pragma unroll
     for (int i = 0; i < P; ++i) acc[i] = f32x2(0);
 
+    // The solve units of a batch are dealt to the four schedulers (warp % 4) so that FFMA2 work + fp64 solve work per
+    // scheduler is even: in this kernel the solve is HALF of the instructions (ncu: 353 per voxel incl. conversions,
+    // addressing and stores, against 365 for gather + march), so a scheduler with five marching warps takes 7 of the 32
+    // units and one with four takes 9 (round robin over the warps gave 9,9,7,7: the wrong way round).
+    constexpr int NU = RB * TX / 32;
+    constexpr int C0 = NPAIR == 2 ? 7 : 3, C1 = NPAIR == 2 ? 7 : 4, C2 = NPAIR == 2 ? 9 : 5;
+    static_assert(NPAIR == 1 || NPAIR == 2, "unit table");
     auto solve_batch = [&](int bb) {
+        const int w = threadIdx.x >> 5, sch = w & 3, nws = (NW - sch + 3) >> 2;      // (derived here: not live across the marches)
+        const int u_begin = (sch == 0 ? 0 : (sch == 1 ? C0 : (sch == 2 ? C0 + C1 : C0 + C1 + C2))) + (w >> 2);
+        const int u_end = sch == 0 ? C0 : (sch == 1 ? C0 + C1 : (sch == 2 ? C0 + C1 + C2 : NU));
 #pragma unroll 1
-        for (int unit = warp; unit < RB * TX / 32; unit += NW)
+        for (int unit = u_begin; unit < u_end; unit += nws)
             solve_unit_voxels<float, NCH, TX, R>(park, PARKROW, bb, unit, lane, cs0, nout, g.n_c, (int64_t)o * g.stride_o, g.stride_m, m0,
                                                  a.vx, a.vy, a.vz, a.rel, 0);
     };
