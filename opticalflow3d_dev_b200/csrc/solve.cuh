@@ -35,6 +35,17 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
     return y;
 }
 
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Smallest eigenvalue of the symmetric matrix [[xx,xy,xz],[xy,yy,yz],[xz,yz,zz]].
 // The reference runs LAPACK cgeev on complex64 (float32 accuracy); for a real symmetric matrix the
 // eigenvalues are real and the lexicographic complex minimum is the smallest one, which is what this
@@ -64,29 +75,37 @@ __device__ __forceinline__ double min_eig_sym3(double xx, double xy, double xz, 
     const double p = p2 * ip;
     const double ba = a * ip, bb = b * ip, bc = c * ip, bxy = xy * ip, bxz = xz * ip, byz = yz * ip;
     double r = 0.5 * (ba * (bb * bc - byz * byz) - bxy * (bxy * bc - byz * bxz) + bxz * (bxy * byz - bb * bxz));
-    r = fmin(1.0, fmax(-1.0, r));
+    // (clamps by compare + select: fmin / fmax on doubles are eight instructions each for the sake of a NaN that the
+    // finite window sums never produce)
+    r = r > 1.0 ? 1.0 : r;
+    r = r < -1.0 ? -1.0 : r;
     const double e = 1.0 - r;
     const float ef = fmaxf((float)e, 1e-30f);
-    float sf = -ef * rsqrtf(ef * 6.0f);              // -sqrt(e/6)
+    // The fp32 seed runs on the hardware approximations themselves (MUFU.RSQ / MUFU.RCP, arguments >= 6e-30 are normal):
+    // rsqrtf() and __frcp_rn() wrap them in denormal scaling and an IEEE fix-up path behind a branch -- a third of the
+    // instructions of this function and three breaks in its instruction schedule -- for last bits that the Newton steps
+    // below do not need.
+    float sf = -ef * rsqrt_approx(ef * 6.0f);        // -sqrt(e/6)
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
         const float d = 6.0f - 4.0f * sf;            // in [6, 8]
-        sf = -ef * rsqrtf(ef * d);                   // -sqrt(e/d)
+        sf = -ef * rsqrt_approx(ef * d);             // -sqrt(e/d)
     }
     // two Newton steps in fp32 (FP32 pipe, off the FP64 dependency chain): relative error ~1e-7
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
         const float f = fmaf(sf * sf, fmaf(4.0f, sf, -6.0f), ef);
         const float fp = 12.0f * sf * (sf - 1.0f);   // > 0 for s < 0
-        sf = fminf(-0.0f, sf - f * __frcp_rn(fmaxf(fp, 1e-30f)));
+        sf = fminf(-0.0f, sf - f * rcp_approx(fmaxf(fp, 1e-30f)));
     }
     double s = (double)sf;
     {   // one Newton step in fp64: quadratic convergence takes 1e-7 to ~1e-14
         const double f = s * s * (4.0 * s - 6.0) + e;
         const double fp = 12.0 * s * (s - 1.0);
-        s -= f * (double)__frcp_rn(fmaxf((float)fp, 1e-30f));
+        s -= f * (double)rcp_approx(fmaxf((float)fp, 1e-30f));
     }
-    s = fmin(0.0, fmax(-0.5, s));
+    s = s > 0.0 ? 0.0 : s;
+    s = s < -0.5 ? -0.5 : s;
     const double lam = (q - p) + 2.0 * p * s;
     return scalar ? q : lam;
 }
