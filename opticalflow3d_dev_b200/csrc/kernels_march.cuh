@@ -141,6 +141,58 @@ __device__ __forceinline__ T ring_push(T (&acc)[P], const Taps<T, K>& f, const T
     return acc[(ph - R + 2 * P) % P];
 }
 
+// ---- the SHIFTING ring -------------------------------------------------------------------------------------------
+// acc[i] holds the partial sum of the output that completes i steps from now.  A step with input v is
+//     acc[i] = fma(w[K - 1 - i], v, acc[i + 1])   (i = 0 .. K - 2, in this order),     acc[K - 1] = w[0] * v
+// -- the FMA writes a different register than it reads, so the ring advances by itself: the same K instructions serve
+// every step.  No unrolled period (the statically rotated ring above is P x K FMAs of code: 44 KB for a 49-tap window
+// against a 32 KB instruction cache), K accumulators instead of P, any number of steps per stage.  An output receives
+// the same operations in the same order as in ring_push (tap 0 by a multiplication, then taps 1 .. K - 1 by FMAs as the
+// inputs arrive): the results are bit-identical.
+__device__ __forceinline__ void fma_to(double& dst, double w, double v, double src) { asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(dst) : "d"(w), "d"(v), "d"(src)); }
+__device__ __forceinline__ void fma_to(float& dst, float w, float v, float src) { asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(dst) : "f"(w), "f"(v), "f"(src)); }
+__device__ __forceinline__ void fma_to(f32x2& dst, f32x2 w, f32x2 v, f32x2 src) { asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dst.u) : "l"(w.u), "l"(v.u), "l"(src.u)); }
+
+template <typename T, int K, int SYM>
+__device__ __forceinline__ T shift_push(T (&acc)[K], const Taps<T, K>& f, const T v) {
+    constexpr int R = K / 2;
+    const T vn = SYM < 0 ? -v : v;
+#pragma unroll
+    for (int i = 0; i < K - 1; ++i) {
+        const int k = K - 1 - i;
+        const bool mirror = SYM != 0 && k > R;
+        fma_to(acc[i], f.w[mirror ? K - 1 - k : k], mirror ? vn : v, acc[i + 1]);
+    }
+    mul_acc(acc[K - 1], f.w[0], v);
+    return acc[0];
+}
+// The same step at either end of a march: step s lies d = s - nout steps into the tail; tap k feeds the output s - k
+// planes after the first one of the range, so only the taps d < k <= s feed outputs inside it (callers may pass the
+// largest s and the smallest d of a group of steps: one set of tests for all of them).  The others are skipped in
+// groups of G accumulators behind warp-uniform branches: the warm-up triangle at the front, its mirror image at the tail
+// and the steps a march is padded by, K (K - 1) / 2 FMAs each.  (A skipped accumulator keeps a stale value: it belongs
+// to an output outside the range, which is never stored, and valid sums only ever read valid sums.)
+template <typename T, int K, int SYM, int G>
+__device__ __forceinline__ T shift_push_edge(T (&acc)[K], const Taps<T, K>& f, const T v, const int s, const int d) {
+    constexpr int R = K / 2;
+    const T vn = SYM < 0 ? -v : v;
+#pragma unroll
+    for (int ib = 0; ib < K; ib += G) {
+        // accumulators [ib, ib + G) take the taps K - 1 - ib down to K - ib - G
+        if (K - 1 - ib > d && K - ib - G <= s) {
+#pragma unroll
+            for (int i = ib; i < (ib + G < K ? ib + G : K); ++i) {
+                const int k = K - 1 - i;
+                const bool mirror = SYM != 0 && k > R;
+                const T w = f.w[mirror ? K - 1 - k : k];
+                if (i == K - 1) mul_acc(acc[i], w, v);
+                else fma_to(acc[i], w, mirror ? vn : v, acc[i + 1 < K ? i + 1 : i]);
+            }
+        }
+    }
+    return acc[0];
+}
+
 // The same step in a stage at the TAIL of a march, with the useless taps skipped in groups of G behind warp-uniform
 // branches.  Step s lies d = s - nout steps into the tail; tap k feeds the output s - k planes after the first one of the
 // range, so the taps k <= d only feed outputs beyond it: the mirror image of the warm-up triangle, K (K - 1) / 2 FMAs at a

@@ -483,7 +483,9 @@ __device__ __forceinline__ void strip_march_batch(T (&acc)[P], const Taps<T, K>&
 // COMPACT (fp64 windows longer than 25 taps): one copy of the gather and of the solve in the instruction stream, the
 // batch of the period selected by a uniform switch -- the fully unrolled period of the 49-tap kernel is 155 KB of SASS
 // (7 copies of a 392-DFMA gather) and stalls 1.6 cycles per issue on instruction fetch.
-template <typename T, int K, int P, int NCH, int NHALF, bool PROD>
+// SHIFT: the y march runs on the shifting accumulator ring (kernels_march.cuh shift_push): K accumulators instead of P,
+// one copy of gather + march + solve in the instruction stream whatever the window length.
+template <typename T, int K, int P, int NCH, int NHALF, bool PROD, bool SHIFT = false>
 __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const StripArgs<T, K> a) {
     constexpr int RB = kStripRB, R = K / 2, TX = 32 * NHALF;
     constexpr int PARKROW = strip_parkrow<NCH, NHALF>();
@@ -519,9 +521,6 @@ __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const 
         st.src[0] = a.in[0] + (int64_t)o * g.stride_o + (int64_t)ch * g.vol;
     }
     T* const m_dst = park + ch * TX + 32 * half + lane;
-    T acc[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) acc[i] = T(0);
 
     auto solve_batch = [&](int bb) {
 #pragma unroll 1
@@ -534,6 +533,34 @@ __global__ void __launch_bounds__(NCH * NHALF * 32, 1) strip_window_solve(const 
     };
 
     st.issue(0);
+    if constexpr (SHIFT) {
+        T accs[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) accs[i] = T(0);
+        const int nb = (nout + 2 * R + RB - 1) / RB;                         // whole batches
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            cp_async_wait<0>();
+            __syncwarp();                                                     // this warp's rows of batch b have landed
+            st.template gather<K, PROD>(a.f, 0);
+            __syncwarp();                                                     // gathered rows visible; input rows free
+            st.issue(b + 1);                                                  // prefetch (clamped addresses: always valid)
+            T* pk = m_dst + (b & 1) * RB * PARKROW;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const T res = shift_push<T, K, 1>(accs, a.f, st.gathered(r));
+                constexpr int kBias = (2 * R + RB - 1) / RB * RB;
+                pk[((r + kBias - 2 * R) % RB) * PARKROW] = res;
+            }
+            __syncthreads();                                                  // one batch of outputs parked by all channels
+            solve_batch(b);
+        }
+        cp_async_wait<0>();
+        return;
+    }
+    T acc[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) acc[i] = T(0);
     int b = 0;
     constexpr bool COMPACT = sizeof(T) == 8 && K > 25;
     if constexpr (COMPACT) {

@@ -205,4 +205,78 @@ __global__ void __launch_bounds__((9 * NG + 1) * 32, MINB) march_window_tma(cons
     }
 }
 
+// The same kernel on the SHIFTING ring (kernels_march.cuh shift_push): one loop over the stages, the ZT steps of a stage
+// unrolled, K accumulators.  Interior stages run the plain step; the stages that contain warm-up or tail steps run the
+// copy with the group tests.
+template <typename T, int K, int NG, int MINB = 1>
+__global__ void __launch_bounds__((9 * NG + 1) * 32, MINB) march_window_tma_sh(const WindowArgs<T, K> a, const __grid_constant__ CUtensorMap tm8,
+                                                                             const __grid_constant__ CUtensorMap tm1) {
+    constexpr int R = K / 2, ZT = kTmaZT, ST = kTmaStages, TX = 32 * NG;
+    constexpr int kStageElems = 4 * ZT * TX;                 // [z][volume][x]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* ring = reinterpret_cast<T*>(smem_raw);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t bar_s = ring_s + (uint32_t)(ST * kStageElems * sizeof(T));   // full[ST], empty[ST]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const MarchGeom& g = a.g;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < ST; ++i) { mbar_init(bar_s + 8 * i, 1); mbar_init(bar_s + 8 * (ST + i), 9 * NG); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 9 * NG) {
+        window_tma_producer<T, K, NG>(&tm8, &tm1, g.n_chunks, g.lane_groups, g.chunk, g.m_begin, g.m_end, (int)g.n_march, ring_s, bar_s);
+        return;
+    }
+
+    const int ch = warp % 9, grp = warp / 9;
+    const int ia = ch < 3 ? 1 : (ch < 5 ? 2 : (ch == 5 ? 3 : ch - 5));
+    const int ib = ch < 3 ? ch + 1 : (ch < 5 ? ch - 1 : (ch == 5 ? 3 : 0));
+    const T* sa = ring + ia * TX + grp * 32 + lane;
+    const T* sb = ring + ib * TX + grp * 32 + lane;
+    const int64_t stride_bytes = g.stride_march * (int64_t)sizeof(T);
+
+    T acc[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) acc[i] = T(0);
+
+    const TmaTask t = tma_task<K, NG>(g.n_chunks, g.lane_groups, g.chunk, g.m_begin, g.m_end, blockIdx.x);
+    const int64_t lane0 = (int64_t)t.x0 + grp * 32;
+    const unsigned nvalid = lane0 + lane < g.n_lane ? (unsigned)t.nout : 0u;
+    // store position of the output completed at step s: c0 + s - 2R (plane 0 of the output is m_begin)
+    char* optr = reinterpret_cast<char*>(a.out + (int64_t)ch * g.vol + (int64_t)t.y * g.stride_other + lane0 + lane) +
+                 ((int64_t)(t.c0 - g.m_begin) - 2 * R) * stride_bytes;
+    const int tail0 = a.edge_skip ? t.nout : (1 << 28);       // first step of the tail
+#pragma unroll 1
+    for (int it = 0; it < t.nstages; ++it) {
+        const int slot = it % ST;
+        mbar_wait(bar_s + 8 * slot, (it / ST) & 1);
+        const T* pa = sa + slot * kStageElems;
+        const T* pb = sb + slot * kStageElems;
+        const int s0 = it * ZT;
+        if (s0 >= 2 * R && s0 + ZT - 1 <= tail0) {
+#pragma unroll
+            for (int r = 0; r < ZT; ++r) {
+                const T v = pa[r * 4 * TX] * pb[r * 4 * TX];
+                const T res = shift_push<T, K, 1>(acc, a.f, v);
+                if ((unsigned)(s0 + r - 2 * R) < nvalid) *reinterpret_cast<T*>(optr) = res;
+                optr += stride_bytes;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < ZT; ++r) {
+                const T v = pa[r * 4 * TX] * pb[r * 4 * TX];
+                // (one set of group tests per stage: its last step decides the warm-up taps, its first step the tail taps)
+                const T res = shift_push_edge<T, K, 1, kEdgeGroup>(acc, a.f, v, s0 + ZT - 1, s0 - tail0);
+                if ((unsigned)(s0 + r - 2 * R) < nvalid) *reinterpret_cast<T*>(optr) = res;
+                optr += stride_bytes;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_s + 8 * (ST + slot));
+    }
+}
+
 }  // namespace of3d

@@ -77,11 +77,14 @@ def slab_workspace_bytes(chunk, plane, ts, rw, halo):
 
 
 def auto_chunk(own, plane, ts, rw, halo, budget):
-    """largest chunk (<= own) whose workspace fits `budget` bytes, at least 8 planes"""
-    c = own
-    while c > 8 and slab_workspace_bytes(c, plane, ts, rw, halo) > budget:
-        c = max(8, (c + 1) // 2)
-    return int(c)
+    """chunk (<= own) of the smallest number of equal chunks whose workspace fits `budget` bytes, at least 8 planes
+    (every chunk repeats the z marches over its 2 rw window planes: 64-plane chunks of a 49-tap window march 112 planes
+    for 64, 86-plane chunks 134 for 86)"""
+    for n in range(1, max(1, own // 8) + 1):
+        c = -(-own // n)
+        if c <= 8 or slab_workspace_bytes(c, plane, ts, rw, halo) <= budget:
+            return int(max(c, min(own, 8)))
+    return int(min(own, 8))
 
 
 def exchange_frames_torch(ext, plan, rank, world, group=None):

@@ -142,4 +142,6 @@ def test_zslab_auto_chunk():
     assert multigpu.auto_chunk(64, plane, ts, rw, h, 200e9) == 64
     c = multigpu.auto_chunk(256, plane, ts, rw, h, 60e9)
     assert 8 <= c < 256 and multigpu.slab_workspace_bytes(c, plane, ts, rw, h) <= 60e9 < multigpu.slab_workspace_bytes(2 * c, plane, ts, rw, h)
+    n = -(-256 // c)                                  # equal chunks: the smallest count that fits
+    assert c == -(-256 // n) and (n == 1 or multigpu.slab_workspace_bytes(-(-256 // (n - 1)), plane, ts, rw, h) > 60e9)
     assert multigpu.auto_chunk(256, plane, ts, rw, h, 1e9) == 8

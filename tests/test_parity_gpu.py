@@ -432,6 +432,44 @@ def test_tma_window_march_equals_cp_async_march(precision, shape, monkeypatch):
         assert_flow_close(a[:3], ref[:3], ref[3], 1e-9, 'tma')
 
 
+@pytest.mark.parametrize('shape,wsig', [((7, 70, 10, 64), 4), ((7, 5, 12, 96), 4), ((7, 33, 8, 64), 6), ((7, 61, 6, 64), 8),
+                                        ((7, 9, 6, 128), 8)])
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_tma_shifting_ring_equals_rotated_ring(precision, shape, wsig, monkeypatch):
+    """march_window_tma_sh (shifting accumulator ring, warm-up and tail taps skipped in groups) gives every output the
+    operations of the statically rotated ring in the same order: bit-identical, for windows of 25, 37 and 49 taps and
+    for marches shorter than the window."""
+    from opticalflow3d_dev_b200.synth import make_stack
+    img = make_stack(shape, seed=98, dtype=np.uint16)
+    cf = _cf()
+    monkeypatch.setenv('OF3D_FORCE_TMA', '1')
+    monkeypatch.setenv('OF3D_TMA_RING', '0')
+    a = cf.calc_flow3D(img, 3, 1, wsig, precision=precision, rel_dtype='float64')
+    monkeypatch.setenv('OF3D_TMA_RING', '1')
+    b = cf.calc_flow3D(img, 3, 1, wsig, precision=precision, rel_dtype='float64')
+    monkeypatch.setenv('OF3D_NO_TAIL_SKIP', '1')
+    c = cf.calc_flow3D(img, 3, 1, wsig, precision=precision, rel_dtype='float64')
+    for x, y, z in zip(a, b, c):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+
+
+@pytest.mark.parametrize('shape,wsig', [((7, 6, 70, 100), 4), ((7, 4, 37, 64), 6), ((7, 3, 150, 40), 8), ((7, 2, 9, 33), 8)])
+def test_strip_shifting_ring_equals_rotated_ring(shape, wsig, monkeypatch):
+    """strip_window_solve<SHIFT> (y march on the shifting accumulator ring, one copy of the batch in the instruction stream)
+    against the rotated-ring kernel: bit-identical, whichever of the two is the default for the window length."""
+    from opticalflow3d_dev_b200.synth import make_stack
+    img = make_stack(shape, seed=97, dtype=np.uint16)
+    cf = _cf()
+    monkeypatch.setenv('OF3D_STRIP_SHIFT', '1')
+    a = cf.calc_flow3D(img, 3, 1, wsig, rel_dtype='float64')
+    monkeypatch.setenv('OF3D_STRIP_SHIFT', '0')
+    b = cf.calc_flow3D(img, 3, 1, wsig, rel_dtype='float64')
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    ref = orc.lk_flow3d(img, 3, 1, wsig, rel_mode='float64')
+    assert_flow_close(a[:3], ref[:3], ref[3], 1e-9, 'strip shift')
+
+
 @pytest.mark.parametrize('shape,sig,precision', [
     ((7, 90, 40, 64), (3, 1, 4), 'fp64'),          # nz >= 4 * (R + R_w) = 84: six slabs of 16 planes, the last one short
     ((7, 97, 33, 50), (3, 1, 4), 'fp64'),          # odd sizes (cp.async march), ragged last slab
