@@ -757,7 +757,7 @@ template <int K, int NPAIR> constexpr size_t strip_x2_smem() {
     return 9 * NPAIR * strip_x2_warp_bytes<K, NPAIR>() + (size_t)2 * kStripRB * strip_parkrow<9, 2 * NPAIR>() * sizeof(float);
 }
 
-template <int K, int P, int NPAIR>
+template <int K, int P, int NPAIR, bool SHIFT = false>
 __global__ void __launch_bounds__(9 * NPAIR * 32, 1) strip_window_solve_x2(const StripArgs<float, K> a, const Taps<f32x2, K> f2) {
     constexpr int RB = kStripRB, R = K / 2, NCH = 9, NW = NCH * NPAIR, TX = 64 * NPAIR, XB = kStripXB;
     constexpr int PARKROW = strip_parkrow<NCH, 2 * NPAIR>();
@@ -787,9 +787,6 @@ __global__ void __launch_bounds__(9 * NPAIR * 32, 1) strip_window_solve_x2(const
     st1.init(reinterpret_cast<float*>(wbase) + BUF, cs0 + 64 * pair + 32, m0 - R, g);
     st0.src[0] = st1.src[0] = a.in[0] + (int64_t)o * g.stride_o + (int64_t)ch * g.vol;
     float* const m_dst = park + ch * TX + 64 * pair + lane;
-    f32x2 acc[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) acc[i] = f32x2(0);
 
     // The solve units of a batch are dealt to the four schedulers (warp % 4) so that FFMA2 work + fp64 solve work per
     // scheduler is even: in this kernel the solve is HALF of the instructions (ncu: 353 per voxel incl. conversions,
@@ -810,6 +807,60 @@ __global__ void __launch_bounds__(9 * NPAIR * 32, 1) strip_window_solve_x2(const
 
     st0.issue(0);
     st1.issue(0);
+    // gather along x, both halves at once: lane (row g_r, block g_b) -> 8 consecutive outputs
+    auto gather_x = [&]() {
+        const int g_r = lane >> 2, g_b = lane & 3;
+        const float* r0 = st0.rows + g_r * ROWSTRIDE + g_b;
+        const float* r1 = st1.rows + g_r * ROWSTRIDE + g_b;
+        f32x2 ga[XB];
+#pragma unroll
+        for (int mm = 0; mm < XB + K - 1; ++mm) {
+            const f32x2 v(r0[(mm & 7) * PITCH + (mm >> 3)], r1[(mm & 7) * PITCH + (mm >> 3)]);
+#pragma unroll
+            for (int i = 0; i < XB; ++i) {
+                const int k = mm - i;
+                if (k >= 0 && k < K) {
+                    const f32x2 w = f2.w[k > R ? K - 1 - k : k];      // symmetric window: half of the taps
+                    if (k == 0) mul_acc(ga[i], w, v); else fma_acc(ga[i], w, v);
+                }
+            }
+        }
+        f32x2* d = xw2 + g_r * kXwRow + g_b * (XB + 1);
+#pragma unroll
+        for (int i = 0; i < XB; ++i) d[i] = ga[i];
+    };
+    if constexpr (SHIFT) {
+        // y march on the shifting ring (kernels_march.cuh shift_push): K packed accumulators, one copy of the batch
+        f32x2 accs[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) accs[i] = f32x2(0);
+        const int nb = (nout + 2 * R + RB - 1) / RB;
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            cp_async_wait<0>();
+            __syncwarp();
+            gather_x();
+            __syncwarp();
+            st0.issue(b + 1);
+            st1.issue(b + 1);
+            float* pk = m_dst + (b & 1) * RB * PARKROW;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const f32x2 res = shift_push<f32x2, K, 1>(accs, f2, xw2[r * kXwRow + lane + lane / 8]);
+                constexpr int kBias = (2 * R + RB - 1) / RB * RB;
+                float* q = pk + ((r + kBias - 2 * R) % RB) * PARKROW;
+                q[0] = res.lo();
+                q[32] = res.hi();
+            }
+            __syncthreads();
+            solve_batch(b);
+        }
+        cp_async_wait<0>();
+        return;
+    }
+    f32x2 acc[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) acc[i] = f32x2(0);
     int b = 0;
 #pragma unroll 1
     for (int s0 = 0; s0 < nsteps; s0 += P) {
@@ -817,28 +868,7 @@ __global__ void __launch_bounds__(9 * NPAIR * 32, 1) strip_window_solve_x2(const
         for (int bi = 0; bi < P / RB; ++bi, ++b) {
             cp_async_wait<0>();
             __syncwarp();                                                     // this warp's rows of batch b have landed
-            {
-                // ---------------- gather along x, both halves at once: lane (row g_r, block g_b) -> 8 consecutive outputs
-                const int g_r = lane >> 2, g_b = lane & 3;
-                const float* r0 = st0.rows + g_r * ROWSTRIDE + g_b;
-                const float* r1 = st1.rows + g_r * ROWSTRIDE + g_b;
-                f32x2 ga[XB];
-#pragma unroll
-                for (int mm = 0; mm < XB + K - 1; ++mm) {
-                    const f32x2 v(r0[(mm & 7) * PITCH + (mm >> 3)], r1[(mm & 7) * PITCH + (mm >> 3)]);
-#pragma unroll
-                    for (int i = 0; i < XB; ++i) {
-                        const int k = mm - i;
-                        if (k >= 0 && k < K) {
-                            const f32x2 w = f2.w[k > R ? K - 1 - k : k];      // symmetric window: half of the taps
-                            if (k == 0) mul_acc(ga[i], w, v); else fma_acc(ga[i], w, v);
-                        }
-                    }
-                }
-                f32x2* d = xw2 + g_r * kXwRow + g_b * (XB + 1);
-#pragma unroll
-                for (int i = 0; i < XB; ++i) d[i] = ga[i];
-            }
+            gather_x();
             __syncwarp();                                                     // gathered rows visible; input rows free
             st0.issue(b + 1);                                                 // prefetch (clamped addresses: always valid)
             st1.issue(b + 1);
