@@ -238,8 +238,9 @@ constexpr size_t conv2_smem(int wpb) {
 }
 
 // SYMG / SYMA: +1 symmetric, -1 antisymmetric taps (only half of them are read)
-template <typename T, int KG, int SYMG, int KA, int SYMA, int WPB, bool V16 = false>
-__global__ void __launch_bounds__(WPB * 32) strip_conv2(const Conv2Args<T, KG, KA> a) {
+// SHIFT: y march on the shifting ring (kernels_march.cuh shift_push): KA accumulators, one copy of the batch; MINB: blocks per SM
+template <typename T, int KG, int SYMG, int KA, int SYMA, int WPB, bool V16 = false, bool SHIFT = false, int MINB = 1>
+__global__ void __launch_bounds__(WPB * 32, MINB) strip_conv2(const Conv2Args<T, KG, KA> a) {
     constexpr int RB = kStripRB, RA = KA / 2, P = (KA + RB - 1) / RB * RB;
     using Stage = typename std::conditional<V16, StripStage16<typename std::conditional<V16, T, double>::type, KG>, StripStage<T, KG, 1, 2>>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -263,12 +264,39 @@ __global__ void __launch_bounds__(WPB * 32) strip_conv2(const Conv2Args<T, KG, K
     else st.src[0] = a.in + (int64_t)o * g.stride_o;
     T* const op = a.out + (int64_t)o * g.stride_o + cw0 + lane;
 
+    st.issue(0);
+    st.issue(1);
+    if constexpr (SHIFT) {
+        T accs[KA];
+#pragma unroll
+        for (int i = 0; i < KA; ++i) accs[i] = T(0);
+        const int nb = (nout + 2 * RA + RB - 1) / RB;
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            cp_async_wait<1>();
+            __syncwarp();
+            if constexpr (V16) {
+                st.fix_edges(b);
+                st.template gather<KG, SYMG>(a.fg, b);
+            } else {
+                st.template gather<KG, false>(a.fg, 0, b);
+            }
+            __syncwarp();
+            st.issue(b + 2);
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int s = b * RB + r;
+                const T res = shift_push<T, KA, SYMA>(accs, a.fa, st.gathered(r));
+                if ((unsigned)(s - 2 * RA) < nvalid) op[(int64_t)(m0 + s - 2 * RA) * g.stride_m] = res;
+            }
+            __syncwarp();
+        }
+        cp_async_wait<0>();
+        return;
+    }
     T acc[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) acc[i] = T(0);
-
-    st.issue(0);
-    st.issue(1);
     int b = 0;
 #pragma unroll 1
     for (int s0 = 0; s0 < nsteps; s0 += P) {
@@ -311,8 +339,8 @@ struct Conv2DualArgs {
     T* out_dx;      // S_y D_x in
 };
 
-template <typename T, int KR, int KS, int WPB, bool V16 = false>
-__global__ void __launch_bounds__(WPB * 32) strip_conv2_dual(const Conv2DualArgs<T, KR, KS> a) {
+template <typename T, int KR, int KS, int WPB, bool V16 = false, bool SHIFT = false, int MINB = 1>
+__global__ void __launch_bounds__(WPB * 32, MINB) strip_conv2_dual(const Conv2DualArgs<T, KR, KS> a) {
     constexpr int RB = kStripRB, R = KR / 2, RS = KS / 2, P = (KR + RB - 1) / RB * RB;
     using Stage = typename std::conditional<V16, StripStage16<typename std::conditional<V16, T, double>::type, KR>, StripStage<T, KR, 1, 2>>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -338,12 +366,47 @@ __global__ void __launch_bounds__(WPB * 32) strip_conv2_dual(const Conv2DualArgs
     T* const oy = a.out_dy + obase;
     T* const ox = a.out_dx + obase;
 
+    st.issue(0);
+    st.issue(1);
+    if constexpr (SHIFT) {
+        T accYs[KR], accXs[KS];                                               // 26 accumulators for 19 / 7 taps instead of 48
+#pragma unroll
+        for (int i = 0; i < KR; ++i) accYs[i] = T(0);
+#pragma unroll
+        for (int i = 0; i < KS; ++i) accXs[i] = T(0);
+        const int nb = (nout + 2 * R + RB - 1) / RB;
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            cp_async_wait<1>();
+            __syncwarp();
+            if constexpr (V16) { st.fix_edges(b); st.template gather<KS, 1>(a.fS, b); }
+            else st.template gather<KS, false>(a.fS, 0, b);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {                                     // dy = D_y (S_x in): row m0 + s - 2R
+                const int s = b * RB + r;
+                const T res = shift_push<T, KR, -1>(accYs, a.fD, st.gathered(r));
+                if ((unsigned)(s - 2 * R) < nvalid) oy[(int64_t)(m0 + s - 2 * R) * g.stride_m] = res;
+            }
+            __syncwarp();
+            if constexpr (V16) st.template gather<KR, -1>(a.fD, b);
+            else st.template gather<KR, false>(a.fD, 0, b);
+            __syncwarp();
+            st.issue(b + 2);
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {                                     // dx = S_y (D_x in): row m0 + s - R - RS
+                const int s = b * RB + r;
+                const T res = shift_push<T, KS, 1>(accXs, a.fS, st.gathered(r));
+                if ((unsigned)(s - R - RS) < nvalid) ox[(int64_t)(m0 + s - R - RS) * g.stride_m] = res;
+            }
+            __syncwarp();
+        }
+        cp_async_wait<0>();
+        return;
+    }
     T accY[P], accX[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) { accY[i] = T(0); accX[i] = T(0); }
-
-    st.issue(0);
-    st.issue(1);
     int b = 0;
 #pragma unroll 1
     for (int s0 = 0; s0 < nsteps; s0 += P) {

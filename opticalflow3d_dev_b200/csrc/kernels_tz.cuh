@@ -192,8 +192,10 @@ struct TzSrcPre {
 
 // One warp per (y row, 32 x columns, z chunk).  Step s consumes input plane c0 - R + s (clamped to the volume): the
 // G and D rings (radius R) complete output c0 + s - 2R, the S ring (radius RS) output c0 + s - R - RS.
-template <typename Src, typename T, int KR, int KS, int P, int WPB>
-__global__ void __launch_bounds__(WPB * 32, (sizeof(T) == 8 && P > 24) ? 2 : 3) march_tz(const TzArgs<T, KR, KS> a) {
+// SHIFT: the three marches run on shifting rings (kernels_march.cuh shift_push): 2 KR + KS accumulators instead of 3 P, one
+// copy of a batch in the instruction stream.
+template <typename Src, typename T, int KR, int KS, int P, int WPB, bool SHIFT = false, int MINB = 0>
+__global__ void __launch_bounds__(WPB * 32, MINB ? MINB : ((sizeof(T) == 8 && P > 24) ? 2 : 3)) march_tz(const TzArgs<T, KR, KS> a) {
     constexpr int R = KR / 2, RS = KS / 2, ZB = kTzBatch;
     static_assert(P >= KR && KR >= KS && P % ZB == 0, "bad unroll period");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -218,9 +220,6 @@ __global__ void __launch_bounds__(WPB * 32, (sizeof(T) == 8 && P > 24) ? 2 : 3) 
     src.issue_batch(0);
     src.issue_batch(1);
 
-    T accG[P], accD[P], accS[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) { accG[i] = T(0); accD[i] = T(0); accS[i] = T(0); }
     // the three output pointers of the plane the R rings complete at step s (plane 0 of the outputs is m_begin); the S
     // ring runs R - RS planes ahead
     const int64_t ostride = g.stride_march * (int64_t)sizeof(T);
@@ -229,6 +228,43 @@ __global__ void __launch_bounds__(WPB * 32, (sizeof(T) == 8 && P > 24) ? 2 : 3) 
     char* pD = reinterpret_cast<char*>(a.out[2]) + o0;
     char* pS = reinterpret_cast<char*>(a.out[1]) + o0 + (int64_t)(R - RS) * ostride;
 
+    if constexpr (SHIFT) {
+        T sG[KR], sD[KR], sS[KS];
+#pragma unroll
+        for (int i = 0; i < KR; ++i) { sG[i] = T(0); sD[i] = T(0); }
+#pragma unroll
+        for (int i = 0; i < KS; ++i) sS[i] = T(0);
+        const int nb = (nout + 2 * R + ZB - 1) / ZB;
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            cp_async_wait<1>();
+            if (Src::kCrossLane) __syncwarp();
+            src.convert(b, a.tt);
+            if (Src::kCrossLane) __syncwarp();
+            if (Src::kCrossLane) src.issue_batch(b + 2);
+#pragma unroll
+            for (int r = 0; r < ZB; ++r) {
+                const int s = b * ZB + r;
+                T vi, vd;
+                src.value(b, r, vi, vd);
+                const T rG = shift_push<T, KR, 1>(sG, a.fG, vd);
+                const T rD = shift_push<T, KR, -1>(sD, a.fD, vi);
+                const T rS = shift_push<T, KS, 1>(sS, a.fS, vi);
+                if ((unsigned)(s - 2 * R) < nvalid) {
+                    *reinterpret_cast<T*>(pG) = rG;
+                    *reinterpret_cast<T*>(pD) = rD;
+                }
+                if ((unsigned)(s - R - RS) < nvalid) *reinterpret_cast<T*>(pS) = rS;
+                pG += ostride; pD += ostride; pS += ostride;
+            }
+            if (!Src::kCrossLane) src.issue_batch(b + 2);
+        }
+        cp_async_wait<0>();
+        return;
+    }
+    T accG[P], accD[P], accS[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) { accG[i] = T(0); accD[i] = T(0); accS[i] = T(0); }
     int b = 0;
 #pragma unroll 1
     for (int s0 = 0; s0 < nsteps; s0 += P) {

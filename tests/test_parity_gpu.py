@@ -453,6 +453,25 @@ def test_tma_shifting_ring_equals_rotated_ring(precision, shape, wsig, monkeypat
         assert np.array_equal(x, y) and np.array_equal(x, z)
 
 
+@pytest.mark.parametrize('shape,sig', [((7, 40, 50, 64), (3, 1, 4)), ((7, 9, 33, 41), (2, 1, 2)), ((7, 70, 8, 32), (1, 1, 2)),
+                                       ((7, 90, 72), (1.5, 1, 4))])
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_gradient_stage_shifting_rings_equal_rotated_rings(precision, shape, sig, monkeypatch):
+    """march_tz<SHIFT>, strip_conv2<SHIFT> and strip_conv2_dual<SHIFT> (gradient z march and in-plane marches on shifting
+    accumulator rings) against the rotated-ring kernels: bit-identical flow in 3D and 2D, fp64 and fp32."""
+    from opticalflow3d_dev_b200.synth import make_stack
+    img = make_stack(shape, seed=96, dtype=np.uint16)
+    cf = _cf()
+    fn = cf.calc_flow3D if len(shape) == 4 else cf.calc_flow2D
+    outs = []
+    for v in ('1', '0'):
+        monkeypatch.setenv('OF3D_TZ_SHIFT', v)
+        monkeypatch.setenv('OF3D_CONV2_SHIFT', v)
+        outs.append(fn(img, *sig, precision=precision))
+    for x, y in zip(*outs):
+        assert np.array_equal(x, y, equal_nan=True)
+
+
 @pytest.mark.parametrize('shape,wsig', [((7, 6, 70, 100), 4), ((7, 4, 37, 64), 6), ((7, 3, 150, 40), 8), ((7, 2, 9, 33), 8)])
 def test_strip_shifting_ring_equals_rotated_ring(shape, wsig, monkeypatch):
     """strip_window_solve<SHIFT> (y march on the shifting accumulator ring, one copy of the batch in the instruction stream)
