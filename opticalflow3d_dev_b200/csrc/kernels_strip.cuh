@@ -21,6 +21,10 @@
 
 namespace of3d {
 
+#ifndef OF3D_EIG32
+#define OF3D_EIG32 1
+#endif
+constexpr bool kEig32 = OF3D_EIG32 != 0;   // fp32 mode: reliability (smallest eigenvalue) in float32 (solve.cuh min_eig_sym3_f32)
 constexpr int kStripRB = 8;    // rows per batch
 constexpr int kStripXB = 8;    // outputs per lane in the gather phase
 
@@ -509,7 +513,7 @@ __device__ __forceinline__ void solve_unit_voxels(const T* park, int parkrow, in
         Flow3 rr[NU];
 #pragma unroll
         for (int u = 0; u < NU; ++u)           // parked values of masked voxels are finite garbage at worst: solved, not stored
-            rr[u] = solve3<false>((double)qv[u][0], (double)qv[u][TX], (double)qv[u][2 * TX], (double)qv[u][3 * TX], (double)qv[u][4 * TX],
+            rr[u] = solve3<false, sizeof(T) == 4 && kEig32>((double)qv[u][0], (double)qv[u][TX], (double)qv[u][2 * TX], (double)qv[u][3 * TX], (double)qv[u][4 * TX],
                                   (double)qv[u][5 * TX], (double)qv[u][6 * TX], (double)qv[u][7 * TX], (double)qv[u][8 * TX]);
 #pragma unroll
         for (int u = 0; u < NU; ++u)

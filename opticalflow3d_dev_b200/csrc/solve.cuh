@@ -110,9 +110,38 @@ __device__ __forceinline__ double min_eig_sym3(double xx, double xy, double xz, 
     return scalar ? q : lam;
 }
 
+// The same in float32, for the fp32 mode (whose reliability is float32, like the reference's: LAPACK cgeev on complex64):
+// the fp64 version is a chain of ~70 dependent operations at DFMA latency and half of the packed fp32 window kernel's
+// instructions.  Error ~ a few eps32 * lambda_max (the fp32 mode's bar is 1e-4 * lambda_max).
+__device__ __forceinline__ float min_eig_sym3_f32(float xx, float xy, float xz, float yy, float yz, float zz) {
+    const float q = (xx + yy + zz) * (1.0f / 3.0f);
+    const float a = xx - q, b = yy - q, c = zz - q;
+    const float p1 = xy * xy + xz * xz + yz * yz;
+    const float p2 = (a * a + b * b + c * c + 2.0f * p1) * (1.0f / 6.0f);
+    const bool scalar = !(p2 > 1e-30f);
+    const float ip = rsqrt_approx(scalar ? 1.0f : p2);
+    const float p = p2 * ip;
+    const float ba = a * ip, bb = b * ip, bc = c * ip, bxy = xy * ip, bxz = xz * ip, byz = yz * ip;
+    float r = 0.5f * (ba * (bb * bc - byz * byz) - bxy * (bxy * bc - byz * bxz) + bxz * (bxy * byz - bb * bxz));
+    r = fminf(1.0f, fmaxf(-1.0f, r));
+    const float ef = fmaxf(1.0f - r, 1e-30f);
+    float sf = -ef * rsqrt_approx(ef * 6.0f);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) sf = -ef * rsqrt_approx(ef * (6.0f - 4.0f * sf));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const float f = fmaf(sf * sf, fmaf(4.0f, sf, -6.0f), ef);
+        const float fp = 12.0f * sf * (sf - 1.0f);
+        sf = fminf(-0.0f, sf - f * rcp_approx(fmaxf(fp, 1e-30f)));
+    }
+    sf = fmaxf(-0.5f, sf);
+    const float lam = (q - p) + 2.0f * p * sf;
+    return scalar ? q : lam;
+}
+
 // EXACT = true reproduces NumPy's evaluation order with individually rounded operations
 // (no FMA contraction), so that given bit-identical window sums the flow is bit-identical.
-template <bool EXACT>
+template <bool EXACT, bool EIG32 = false>
 __device__ __forceinline__ Flow3 solve3(double xx, double xy, double xz, double yy, double yz, double zz,
                                         double tx, double ty, double tz) {
     Flow3 o;
@@ -143,7 +172,8 @@ __device__ __forceinline__ Flow3 solve3(double xx, double xy, double xz, double 
         o.vy = ninv * (cxy * tx + cyy * ty + cyz * tz);
         o.vz = ninv * (cxz * tx + cyz * ty + czz * tz);
     }
-    o.rel = min_eig_sym3(xx, xy, xz, yy, yz, zz);
+    if (EIG32) o.rel = (double)min_eig_sym3_f32((float)xx, (float)xy, (float)xz, (float)yy, (float)yz, (float)zz);
+    else o.rel = min_eig_sym3(xx, xy, xz, yy, yz, zz);
     return o;
 }
 
