@@ -726,20 +726,25 @@ __global__ void __launch_bounds__(5 * NQ * 32, 1) strip_window_solve_2d(const St
     const int nsteps = (nout + 2 * R + P - 1) / P * P;
     const int64_t plane_off = (int64_t)o * g.stride_o;
 
-    // a task = 8 consecutive elements (one per lane of a quarter-warp) of one row of one gradient
+    // A quarter-warp fetches a piece of 8 consecutive elements (one per lane) of one row of one gradient.  The 4 NW
+    // quarter-warps of the block form RPI rows of NI pieces: which piece (column, destination) a thread fetches is fixed for
+    // the whole march, only the row task (gradient, row of the batch) advances -- no division in the loop.
+    constexpr int RPI = (4 * NW) / L::NI > 0 ? (4 * NW) / L::NI : 1, NRT = 3 * RB;
+    static_assert(L::NI <= 4 * NW, "a row of pieces must fit the block's quarter-warps");
+    const int qw = warp * 4 + (lane >> 3);
+    const int is_rr = qw / L::NI, is_i = qw - is_rr * L::NI, is_e = 8 * is_i + (lane & 7);
+    const bool is_on = is_rr < RPI && (L::RL % 8 == 0 || is_e < L::RL);
+    const int is_c = max(0, min(cs0 - R + is_e, g.n_c - 1));                 // clamped source column (mode='nearest')
+    const int is_d = (lane & 7) * PITCH + is_i;                              // element offset inside a staged row
     auto issue = [&](int b) {
-        constexpr int NTASK = 3 * RB * L::NI;
-        const int l8 = lane & 7;
+        if (is_on) {
 #pragma unroll 1
-        for (int j = 0; j < (NTASK + 4 * NW - 1) / (4 * NW); ++j) {
-            const int tk = j * 4 * NW + warp * 4 + (lane >> 3);
-            const int i = tk % L::NI, rv = tk / L::NI, r = rv % RB, v = rv / RB;
-            const int e = 8 * i + l8;
-            if (tk < NTASK && (L::RL % 8 == 0 || e < L::RL)) {
+            for (int rt = is_rr; rt < NRT; rt += RPI) {
+                const int v = rt >> 3, r = rt & 7;
+                static_assert(RB == 8, "row task decoding");
                 const int m = max(0, min(m0 - R + b * RB + r, g.n_m - 1));
-                const int c = max(0, min(cs0 - R + e, g.n_c - 1));
-                cp_async_elem<T>(stage_s + (uint32_t)(((b & 1) * L::BUF + v * L::VOLBUF + r * ROWSTRIDE + l8 * PITCH + i) * sizeof(T)),
-                                 a.in[v] + plane_off + (int64_t)m * g.stride_m + c);
+                cp_async_elem<T>(stage_s + (uint32_t)(((b & 1) * L::BUF + v * L::VOLBUF + r * ROWSTRIDE + is_d) * sizeof(T)),
+                                 a.in[v] + plane_off + (int64_t)m * g.stride_m + is_c);
             }
         }
         cp_async_commit();

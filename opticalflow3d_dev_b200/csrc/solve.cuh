@@ -182,6 +182,24 @@ __device__ __forceinline__ Flow3 solve3(double xx, double xy, double xz, double 
 template <bool EXACT>
 __device__ __forceinline__ Flow2 solve2(double xx, double xy, double yy, double tx, double ty) {
     Flow2 o;
+    if (!EXACT) {
+        // Straight-line code: the IEEE reciprocal and square root each hide a fix-up call behind a branch (cf. rcp_fast).  The
+        // determinant and the discriminant keep their individually rounded form, so the SIGN of the discriminant -- NaN or
+        // tiny real, calc_flow.py:166 -- still follows NumPy's.
+        const double det = __dsub_rn(__dmul_rn(xx, yy), __dmul_rn(xy, xy));
+        const double inv = rcp_fast(__dadd_rn(det, kEps));
+        o.vx = inv * (xy * ty - yy * tx);
+        o.vy = inv * (xy * tx - xx * ty);
+        const double tr = __dadd_rn(xx, yy);
+        const double disc = __dsub_rn(__dmul_rn(tr, tr), __dmul_rn(4.0, det));
+        const bool small = disc < 1e-200;                       // rsqrt.approx.ftz would flush a denormal: scale by 4^300
+        const double ds = small ? disc * 0x1p600 : disc;
+        double root = ds * rsqrt_fast(ds);
+        root = ds > 0.0 ? (small ? root * 0x1p-300 : root) : 0.0;
+        // np.minimum of the two roots is the one with the minus sign; a negative discriminant gives NaN like np.sqrt
+        o.rel = disc < 0.0 ? __longlong_as_double(0x7ff8000000000000LL) : 0.5 * (tr - root);
+        return o;
+    }
     const double det = __dsub_rn(__dmul_rn(xx, yy), __dmul_rn(xy, xy));
     const double inv = __drcp_rn(__dadd_rn(det, kEps));
     o.vx = __dmul_rn(inv, __dadd_rn(__dmul_rn(yy, -tx), __dmul_rn(-xy, -ty)));
