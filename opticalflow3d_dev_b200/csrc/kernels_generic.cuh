@@ -165,6 +165,51 @@ __global__ void __launch_bounds__(256) temporal_vec(const FramePtrs frames, cons
     }
 }
 
+// The temporal stage of a BATCH of consecutive output timepoints of a 2D time-lapse in one launch (of3d_flow2d_batch):
+// output timepoint j reads the frames j .. j + KT - 1, so a thread keeps a sliding window of KT 16-byte pieces in registers
+// (rotated statically over an unrolled period of KT timepoints) and loads every frame ONCE -- 2 (n_out + KT - 1) / n_out
+// bytes per pixel instead of 2 KT, and one launch instead of n_out.  8/16-bit frames, paired form only: the arithmetic of
+// temporal_vec, operation for operation (bit-identical results).  frames.p[k] = frame k of the batch; ic / dt0 hold n_out
+// planes of `plane` elements.
+template <typename T, int R>
+struct TapsHalf { T w[R + 1]; };       // w[l] = T[R + l]
+
+template <typename Tin, typename T, int KT>
+__global__ void __launch_bounds__(256) temporal_vec_batch(const FramePtrs frames, const TapsHalf<T, KT / 2> tw, T* __restrict__ ic,
+                                                          T* __restrict__ dt0, int64_t nvec, int n_out, int64_t plane) {
+    constexpr int VEC = 16 / sizeof(Tin), R = KT / 2;
+    static_assert(std::is_integral<Tin>::value && sizeof(Tin) <= 2, "paired integer form");
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 win[KT];                                      // frame j + k of output timepoint j = j0 + u lives in win[(u + k) % KT]
+#pragma unroll
+        for (int k = 0; k < KT - 1; ++k) win[k] = __ldg(reinterpret_cast<const uint4*>(frames.p[k]) + i);
+#pragma unroll 1
+        for (int j0 = 0; j0 < n_out; j0 += KT) {
+#pragma unroll
+            for (int u = 0; u < KT; ++u) {
+                const int j = j0 + u;
+                if (j < n_out) {
+                    win[(u + KT - 1) % KT] = __ldg(reinterpret_cast<const uint4*>(frames.p[j + KT - 1]) + i);
+                    T acc[VEC], c[VEC];
+                    const Tin* vc = reinterpret_cast<const Tin*>(&win[(u + R) % KT]);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) { c[q] = (T)vc[q]; acc[q] = T(0); }
+#pragma unroll
+                    for (int l = 1; l <= R; ++l) {
+                        const Tin* va = reinterpret_cast<const Tin*>(&win[(u + R + l) % KT]);
+                        const Tin* vb = reinterpret_cast<const Tin*>(&win[(u + R - l) % KT]);
+                        const T w = tw.w[l];
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) acc[q] = fma(w, (T)((int)va[q] - (int)vb[q]), acc[q]);
+                    }
+                    store_vec<VEC>(ic + (int64_t)j * plane + i * VEC, c);
+                    store_vec<VEC>(dt0 + (int64_t)j * plane + i * VEC, acc);
+                }
+            }
+        }
+    }
+}
+
 // float64 reliability -> the float32 the reference returns in 3D (calc_flow.py:355-357), one rounding (OF3D_FLAG_REL_F32)
 __global__ void __launch_bounds__(256) narrow_f64_f32(const double* __restrict__ in, float* __restrict__ out, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)

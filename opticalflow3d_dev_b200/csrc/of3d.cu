@@ -373,7 +373,28 @@ static int flow_staged(of3d_ctx* c, int stage, int ndim, const void* const* fram
         char* dt0 = ws_take<char>(c, (size_t)n * ts);
         const Shape s1{2, 1, ny, nx};
         void* none[4] = {nullptr, nullptr, nullptr, nullptr};
-        for (int64_t j = 0; j < nz; ++j) {
+        // all timepoints of the batch in one launch, every frame read once (temporal_vec_batch): 8/16-bit frames, the
+        // reference's default seven temporal taps, 16-byte aligned frames and planes
+        bool batched_t = !(flags & OF3D_FLAG_EXACT) && t->nT == 7 && (in_dtype == OF3D_U8 || in_dtype == OF3D_U16) &&
+                         taps_symmetric(t->T, t->nT, -1.0) && t->T[t->nT / 2] == 0.0 && ((size_t)ny * nx * dtype_size(in_dtype)) % 16 == 0 &&
+                         !getenv("OF3D_NO_BATCHED_T");
+        for (int k = 0; batched_t && k < n_frames; ++k) batched_t = reinterpret_cast<uintptr_t>(fp.p[k]) % 16 == 0;
+        if (batched_t) {
+            const int64_t nvec = ny * nx * (int64_t)dtype_size(in_dtype) / 16;
+            StageScope span(c, OF3D_STAGE_TEMPORAL);
+            auto go = [&](auto tin, auto tt) {
+                using Tin = decltype(tin); using TT = decltype(tt);
+                TapsHalf<TT, 3> tw;
+                for (int l = 0; l <= 3; ++l) tw.w[l] = (TT)t->T[3 + l];
+                temporal_vec_batch<Tin, TT, 7><<<grid_for(c, nvec), 256, 0, c->stream>>>(fp, tw, reinterpret_cast<TT*>(ic), reinterpret_cast<TT*>(dt0),
+                                                                                         nvec, (int)nz, ny * nx);
+            };
+            if (precision == OF3D_FP64) { if (in_dtype == OF3D_U8) go(uint8_t(), double()); else go(uint16_t(), double()); }
+            else { if (in_dtype == OF3D_U8) go(uint8_t(), float()); else go(uint16_t(), float()); }
+            c->launches++;
+            OF3D_CUDA_TRY(cudaGetLastError());
+        }
+        for (int64_t j = 0; !batched_t && j < nz; ++j) {
             FramePtrs fj;
             memset(&fj, 0, sizeof(fj));
             for (int k = 0; k < t->nT; ++k) fj.p[k] = fp.p[j + k];
