@@ -374,19 +374,20 @@ def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, ste
     # ---- (a) the halo planes that arrived are the neighbour's planes (dt mode: the widened centre frame in `ic`)
     halo_ok = True
     kc = zs_.kt // 2
+    dtm = mode in ('dt', 'dt_wide')
 
     def check_halo(z_first, count, got_raw, got_ic, t_raw):
         chk = torch.empty((count, ny, nx), dtype=torch.uint16, device=dev)
         torch.cuda.synchronize()
-        _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, chk.data_ptr(), 1, count, ny, nx, kc if mode == 'dt' else t_raw, z_first, seed), 'synth')
-        return bool(torch.equal(chk.to(got_ic.dtype), got_ic)) if mode == 'dt' else bool(torch.equal(chk, got_raw))
+        _lib.check(ctx.lib.of3d_synth_blobs(ctx.handle, chk.data_ptr(), 1, count, ny, nx, kc if dtm else t_raw, z_first, seed), 'synth')
+        return bool(torch.equal(chk.to(got_ic.dtype), got_ic)) if dtm else bool(torch.equal(chk, got_raw))
 
     if zs_.lo:
-        halo_ok = halo_ok and check_halo(zs_.z0 - zs_.lo, zs_.lo, None if mode == 'dt' else zs_.frames[zs_.kt - 1, :zs_.lo],
-                                         zs_.ic[:zs_.lo] if mode == 'dt' else None, zs_.kt - 1)
+        halo_ok = halo_ok and check_halo(zs_.z0 - zs_.lo, zs_.lo, None if dtm else zs_.frames[zs_.kt - 1, :zs_.lo],
+                                         zs_.ic[:zs_.lo] if dtm else None, zs_.kt - 1)
     if zs_.hi:
-        halo_ok = halo_ok and check_halo(zs_.z1, zs_.hi, None if mode == 'dt' else zs_.frames[0, zs_.lo + zs_.own:],
-                                         zs_.ic[zs_.lo + zs_.own:] if mode == 'dt' else None, 0)
+        halo_ok = halo_ok and check_halo(zs_.z1, zs_.hi, None if dtm else zs_.frames[0, zs_.lo + zs_.own:],
+                                         zs_.ic[zs_.lo + zs_.own:] if dtm else None, 0)
     del tmp
     for _ in range(max(warmup - 1, 0)):
         step()
@@ -433,10 +434,13 @@ def zslab_measure(rank, world, local_rank, sig, nz_total, ny, nx, precision, ste
                    'exchange': mode,
                    'sharding': ('z-slab; temporal stage on the boundary planes, then %d halo planes of (ic, dt0) exchanged with each '
                                 'neighbour by the library (grouped ncclSend/ncclRecv, in place) while the interior temporal stage '
-                                'runs; interior chunks overlap the exchange' % H) if mode == 'dt' else
+                                'runs; interior chunks overlap the exchange' % H) if mode in ('dt', 'dt_wide') else
                                ('z-slab; %d raw halo planes of each of the %d frames exchanged with each neighbour by the '
                                 'library (grouped ncclSend/ncclRecv, in place); interior chunks overlap the exchange' % (H, kt)),
-                   'halo_bytes_sent_per_interior_rank_per_step': int(2 * H * ny * nx * (2 * (8 if precision == 'fp64' else 4) if mode == 'dt' else kt * es))},
+                   # 'dt': dt0 in the compute type + ic as the raw centre planes (8/16-bit frames); 'dt_wide': both in the compute type
+                   'halo_bytes_sent_per_interior_rank_per_step': int(2 * H * ny * nx * (
+                       ((8 if precision == 'fp64' else 4) + es) if mode == 'dt' else
+                       (2 * (8 if precision == 'fp64' else 4) if mode == 'dt_wide' else kt * es)))},
         'parity_small_volume_bit_identical': parity, 'halo_planes_verified': bool(stat[2].item() == 0.0),
         'stages_ms_per_step_rank0': {k: round(v[0] / steps, 3) for k, v in stages.items()},
         'free_hbm_bytes_rank0_after': int(mem[0]),
@@ -819,7 +823,8 @@ def main():
     ap.add_argument('--cpu-voxels', type=int, default=400_000, help='voxels per core per CPU step')
     ap.add_argument('--cpu-cores', type=int, default=None, help='processes of the CPU arm (default 16, or all cores if fewer)')
     ap.add_argument('--chunk-planes', type=int, default=None, help='z-slab runs: owned planes per pass of the slab pipeline (default: as large as the free HBM allows)')
-    ap.add_argument('--zslab-exchange', default='dt', choices=['dt', 'raw'], help="halo exchange of (ic, dt0) or of the raw frames")
+    ap.add_argument('--zslab-exchange', default='dt', choices=['dt', 'dt_wide', 'raw'],
+                    help="halo exchange of (raw centre planes, dt0), of (ic, dt0) in the compute type, or of the raw frames")
     ap.add_argument('--no-zslab', action='store_true', help='multi-GPU runs: skip the z-slab sub-record')
     ap.add_argument('--no-configs', action='store_true', help='single-GPU runs: skip the quick lines of the other BASELINE configs')
     ap.add_argument('--shape', default=None, help='override the workload shape, e.g. 19,128,512,512 (debug)')

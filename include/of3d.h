@@ -212,6 +212,14 @@ OF3D_API int of3d_comm_init(of3d_ctx* ctx, const void* id128, int nranks, int ra
 OF3D_API int of3d_comm_destroy(of3d_ctx* ctx);
 OF3D_API int of3d_halo_exchange(of3d_ctx* ctx, void* const* frames_ext, int n_frames, size_t plane_bytes, int64_t lo, int64_t own,
                                 int64_t hi, int64_t send_dn, int64_t send_up);
+/* The exchange of the (ic, dt0) halos with ic travelling as what it is the widening of: the raw planes of the centre frame
+ * (calc_flow.py:225 `images.astype(np.float64)`; 8/16-bit integer frames): 2 + 8 instead of 8 + 8 bytes per voxel in fp64.
+ * `centre_own`: the `own` planes of the centre frame (DEVICE, in_dtype); `stage`: DEVICE scratch of lo + hi raw planes;
+ * ic_ext / dt0_ext as in of3d_flow3d_slab_dt.  The planes that arrive are widened into the halo planes of ic_ext on the
+ * exchange stream -- the value the neighbour's temporal stage stored, bit for bit. */
+OF3D_API int of3d_halo_exchange_centre(of3d_ctx* ctx, const void* centre_own, int in_dtype, void* stage, void* ic_ext, void* dt0_ext,
+                                       int precision, int64_t plane_elems, int64_t lo, int64_t own, int64_t hi, int64_t send_dn,
+                                       int64_t send_up);
 OF3D_API int of3d_flow3d_slab(of3d_ctx* ctx, const void* const* frames_ext, int in_dtype, int64_t nz_ext, int64_t ny, int64_t nx,
                               int64_t own_lo, int64_t own_n, int64_t chunk_planes, const of3d_taps* taps, int precision,
                               unsigned flags, void* vx, void* vy, void* vz, void* rel);

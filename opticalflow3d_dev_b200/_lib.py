@@ -47,6 +47,7 @@ SIGNATURES = {
     'of3d_comm_init': (_i, [_vp, _vp, _i, _i]),
     'of3d_comm_destroy': (_i, [_vp]),
     'of3d_halo_exchange': (_i, [_vp, C.POINTER(_vp), _i, _sz, _i64, _i64, _i64, _i64, _i64]),
+    'of3d_halo_exchange_centre': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i64, _i64, _i64, _i64, _i64, _i64]),
     'of3d_flow3d_slab': (_i, [_vp, C.POINTER(_vp), _i, _i64, _i64, _i64, _i64, _i64, _i64, C.POINTER(Taps), _i, _u,
                               _vp, _vp, _vp, _vp]),
     'of3d_flow3d_slab_dt': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, C.POINTER(Taps), _i, _u, _vp, _vp, _vp, _vp]),

@@ -210,6 +210,12 @@ __global__ void __launch_bounds__(256) temporal_vec_batch(const FramePtrs frames
     }
 }
 
+// raw halo planes of the centre frame -> the compute type (what the temporal kernels store as ic: an exact widening)
+template <typename Tin, typename T>
+__global__ void __launch_bounds__(256) widen_planes(const Tin* __restrict__ in, T* __restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (T)in[i];
+}
+
 // float64 reliability -> the float32 the reference returns in 3D (calc_flow.py:355-357), one rounding (OF3D_FLAG_REL_F32)
 __global__ void __launch_bounds__(256) narrow_f64_f32(const double* __restrict__ in, float* __restrict__ out, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)

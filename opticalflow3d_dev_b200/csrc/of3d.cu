@@ -968,6 +968,63 @@ OF3D_API int of3d_halo_exchange(of3d_ctx* c, void* const* frames_ext, int n_fram
     return OF3D_OK;
 }
 
+OF3D_API int of3d_halo_exchange_centre(of3d_ctx* c, const void* centre_own, int in_dtype, void* stage, void* ic_ext, void* dt0_ext,
+                                       int precision, int64_t plane_elems, int64_t lo, int64_t own, int64_t hi, int64_t send_dn,
+                                       int64_t send_up) {
+    if (!c || !centre_own || !stage || !ic_ext || !dt0_ext || plane_elems < 1 || lo < 0 || hi < 0 || own < 1 || send_dn < 0 || send_up < 0 ||
+        send_dn > own || send_up > own) { set_error("bad argument"); return OF3D_ERR_ARG; }
+    if (in_dtype != OF3D_U8 && in_dtype != OF3D_U16 && in_dtype != OF3D_I16) { set_error("of3d_halo_exchange_centre takes 8/16-bit integer frames"); return OF3D_ERR_ARG; }
+    if (precision != OF3D_FP64 && precision != OF3D_FP32) { set_error("precision must be OF3D_FP64 or OF3D_FP32"); return OF3D_ERR_ARG; }
+    if (!c->comm) { set_error("of3d_halo_exchange_centre: no communicator (of3d_comm_init)"); return OF3D_ERR_ARG; }
+    NcclApi& n = nccl();
+    OF3D_CUDA_TRY(cudaSetDevice(c->device));
+    const int r = c->comm_rank, last = c->comm_size - 1;
+    const size_t ib = dtype_size(in_dtype), ts = precision == OF3D_FP32 ? 4 : 8;
+    const size_t pr = (size_t)plane_elems * ib, pt = (size_t)plane_elems * ts;      // plane bytes: raw, compute type
+    // the owned planes may still be written by work queued on the compute stream
+    OF3D_CUDA_TRY(cudaEventRecord(c->ev_ready, c->stream));
+    OF3D_CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_ready, 0));
+    const char* cen = static_cast<const char*>(centre_own);
+    char* st = static_cast<char*>(stage);                                          // [lo planes from below][hi planes from above]
+    char* dt = static_cast<char*>(dt0_ext);
+    if (int e = n.GroupStart()) return nccl_fail("ncclGroupStart", e);
+    int err = 0;
+    if (r > 0) {
+        if (send_dn && !err) err = n.Send(cen, (size_t)send_dn * pr, kNcclUint8, r - 1, c->comm, c->s_comm);
+        if (send_dn && !err) err = n.Send(dt + (size_t)lo * pt, (size_t)send_dn * pt, kNcclUint8, r - 1, c->comm, c->s_comm);
+        if (lo && !err) err = n.Recv(st, (size_t)lo * pr, kNcclUint8, r - 1, c->comm, c->s_comm);
+        if (lo && !err) err = n.Recv(dt, (size_t)lo * pt, kNcclUint8, r - 1, c->comm, c->s_comm);
+    }
+    if (r < last) {
+        if (send_up && !err) err = n.Send(cen + (size_t)(own - send_up) * pr, (size_t)send_up * pr, kNcclUint8, r + 1, c->comm, c->s_comm);
+        if (send_up && !err) err = n.Send(dt + (size_t)(lo + own - send_up) * pt, (size_t)send_up * pt, kNcclUint8, r + 1, c->comm, c->s_comm);
+        if (hi && !err) err = n.Recv(st + (size_t)lo * pr, (size_t)hi * pr, kNcclUint8, r + 1, c->comm, c->s_comm);
+        if (hi && !err) err = n.Recv(dt + (size_t)(lo + own) * pt, (size_t)hi * pt, kNcclUint8, r + 1, c->comm, c->s_comm);
+    }
+    const int e2 = n.GroupEnd();
+    if (err) return nccl_fail("ncclSend/ncclRecv", err);
+    if (e2) return nccl_fail("ncclGroupEnd", e2);
+    // widen the raw planes that arrived into the halo planes of ic, on the exchange stream
+    auto widen = [&](const char* src, char* dst, int64_t planes) {
+        if (planes <= 0) return;
+        const int64_t cnt = planes * plane_elems;
+        const int grid = grid_for(c, cnt);
+#define OF3D_WIDEN(TIN) \
+        if (precision == OF3D_FP64) widen_planes<TIN, double><<<grid, 256, 0, c->s_comm>>>(reinterpret_cast<const TIN*>(src), reinterpret_cast<double*>(dst), cnt); \
+        else widen_planes<TIN, float><<<grid, 256, 0, c->s_comm>>>(reinterpret_cast<const TIN*>(src), reinterpret_cast<float*>(dst), cnt);
+        if (in_dtype == OF3D_U8) { OF3D_WIDEN(uint8_t) } else if (in_dtype == OF3D_U16) { OF3D_WIDEN(uint16_t) } else { OF3D_WIDEN(int16_t) }
+#undef OF3D_WIDEN
+        c->launches++;
+    };
+    char* ic = static_cast<char*>(ic_ext);
+    if (r > 0) widen(st, ic, lo);
+    if (r < last) widen(st + (size_t)lo * pr, ic + (size_t)(lo + own) * pt, hi);
+    OF3D_CUDA_TRY(cudaGetLastError());
+    OF3D_CUDA_TRY(cudaEventRecord(c->ev_halo, c->s_comm));
+    c->halo_pending = true;
+    return OF3D_OK;
+}
+
 // The owned range in chunks (interior chunks first: they overlap a halo exchange in flight); frames_ext != nullptr: raw
 // frames, else (ic_ext, dt0_ext) volumes of the compute type
 static int slab_run(of3d_ctx* c, const void* const* frames_ext, const void* ic_ext, const void* dt0_ext, int in_dtype, int64_t nz_ext,

@@ -12,8 +12,10 @@ torch.distributed for the plumbing, the library's own NCCL communicator for the 
   ends of the volume, where the reference's clamp-to-edge applies) -- and
       1. exchanges halo planes with its two neighbours, straight into place: one grouped ncclSend/ncclRecv on the
          library's exchange stream (of3d_halo_exchange), non-periodic.  exchange='dt' (default): the temporal stage
-         (z-local) runs on the boundary planes first, the halos of (ic, dt0) -- 16 bytes per voxel -- travel while the
-         temporal stage of the interior planes runs; exchange='raw': the raw planes of all kt frames (2 kt bytes per
+         (z-local) runs on the boundary planes first, the halos of (ic, dt0) travel while the temporal stage of the
+         interior planes runs -- ic as the raw centre-frame planes it is the widening of for 8/16-bit integer frames
+         (of3d_halo_exchange_centre: 2 + 8 bytes per voxel in fp64; exchange='dt_wide': 8 + 8, both in the compute
+         type); exchange='raw': the raw planes of all kt frames (2 kt bytes per
          voxel: more bytes for kt > 8, but no temporal pass and no (ic, dt0) volumes);
       2. runs of3d_flow3d_slab(_dt): every stage works only on the planes the owned range needs (temporal derivative +
          gradient z pass and in-plane passes on own +- Rw, window sums and solve on own), in chunks of `chunk_planes`
@@ -148,9 +150,12 @@ class ZSlab:
         self.kt = self._keep[3].size
         tdev = torch.device('cuda', self.dev)
         tdt = getattr(torch, self.np_dt.name)
-        if exchange not in ('dt', 'raw'):
-            raise ValueError("exchange must be 'dt' or 'raw'")
-        self.mode = exchange
+        if exchange not in ('dt', 'dt_wide', 'raw'):
+            raise ValueError("exchange must be 'dt', 'dt_wide' or 'raw'")
+        # 'dt': (ic, dt0) halos, ic as the raw centre planes for 8/16-bit integer frames; 'dt_wide': ic in the compute type
+        self.raw_centre = exchange == 'dt' and self.np_dt in (np.dtype(np.uint8), np.dtype(np.uint16), np.dtype(np.int16))
+        self._stage = None
+        self.mode = 'dt' if exchange == 'dt_wide' else exchange
         self.odt = torch.float64 if precision == 'fp64' else torch.float32
         next_ = self.lo + self.own + self.hi
         if self.mode == 'raw':
@@ -234,10 +239,21 @@ class ZSlab:
                     split = (send_dn, self.own - send_up)
                 if self.world > 1:
                     self._init_comm()
-                    ptrs = (C.c_void_p * 2)(self.ic.data_ptr(), self.dt0.data_ptr())
-                    rc = self.ctx.lib.of3d_halo_exchange(self.ctx.handle, ptrs, 2, self.ny * self.nx * self.ic.element_size(),
-                                                         self.lo, self.own, self.hi, send_dn, send_up)
-                    _lib.check(rc, 'of3d_halo_exchange')
+                    if self.raw_centre:
+                        # ic travels as the raw centre planes it is the widening of (2 + 8 instead of 8 + 8 bytes per voxel)
+                        if self._stage is None:
+                            self._stage = torch.empty((max(1, self.lo + self.hi), self.ny, self.nx), dtype=self.frames.dtype,
+                                                      device=self.frames.device)
+                        rc = self.ctx.lib.of3d_halo_exchange_centre(
+                            self.ctx.handle, self.frames[self.kt // 2].data_ptr(), self.code, self._stage.data_ptr(), self.ic.data_ptr(),
+                            self.dt0.data_ptr(), _lib.FP64 if self.precision == 'fp64' else _lib.FP32, self.ny * self.nx, self.lo, self.own,
+                            self.hi, send_dn, send_up)
+                        _lib.check(rc, 'of3d_halo_exchange_centre')
+                    else:
+                        ptrs = (C.c_void_p * 2)(self.ic.data_ptr(), self.dt0.data_ptr())
+                        rc = self.ctx.lib.of3d_halo_exchange(self.ctx.handle, ptrs, 2, self.ny * self.nx * self.ic.element_size(),
+                                                             self.lo, self.own, self.hi, send_dn, send_up)
+                        _lib.check(rc, 'of3d_halo_exchange')
                 if split:
                     self._temporal(*split)
             finally:

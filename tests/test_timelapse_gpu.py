@@ -120,7 +120,7 @@ def _nccl_worker(rank, world, port, shape, sig, seed, chunk, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('chunk,mode', [(None, 'dt'), (8, 'dt'), (None, 'raw'), (8, 'raw')])
+@pytest.mark.parametrize('chunk,mode', [(None, 'dt'), (8, 'dt'), (None, 'dt_wide'), (None, 'raw'), (8, 'raw')])
 def test_zslab_nccl_two_gpus(chunk, mode):
     """z-slab sharding over two B200s: in-library NCCL halo exchange -- of (ic, dt0) after a boundary-first temporal stage,
     or of the raw frames -- + of3d_flow3d_slab(_dt), bit-identical to the single-GPU result (whole slab, and in chunks
